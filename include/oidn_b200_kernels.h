@@ -1,0 +1,97 @@
+/* oidn_b200 kernel-level C ABI.
+ *
+ * This is the boundary a device module in the reference tree binds to: every entry point below is
+ * what one `Engine::new<Op>()` product (core/engine.h:67-75) needs in order to run on a B200, with
+ * plain pointers and sizes only (no C++ or torch types). Each function cites the reference
+ * interface it stands in for. All functions return 0 on success or a negative oidnb200 error
+ * code / positive cudaError_t; oidnb200_last_error() returns a message for the calling thread.
+ *
+ * Tensors: NHWC fp16, N=1, channels padded to a multiple of 16 ("hwc", tensorBlockC=16 in the
+ * reference's vocabulary, core/tensor_layout.h:11-33). Images: the user's strided 1-3 channel
+ * fp32/fp16 pixel buffers exactly as passed to oidnSetSharedFilterImage (core/image.h:14-120).
+ */
+#ifndef OIDN_B200_KERNELS_H
+#define OIDN_B200_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OIDNB200_API __attribute__((visibility("default")))
+
+typedef void* oidnb200_stream; /* cudaStream_t */
+
+enum
+{
+  OIDNB200_OK = 0,
+  OIDNB200_ERR_INVALID = -1,     /* bad descriptor / argument */
+  OIDNB200_ERR_UNSUPPORTED = -2, /* shape cannot be mapped (e.g. weights do not fit in smem) */
+  OIDNB200_ERR_DRIVER = -3       /* driver entry point missing / tensor-map encode failed */
+};
+
+OIDNB200_API const char* oidnb200_last_error(void);
+
+/* Number of CUDA devices with compute capability 10.x; 0 when no driver/GPU is present.
+ * Stands in for CUDADevice::getPhysicalDevices (devices/cuda/cuda_device.cpp:60-101). */
+OIDNB200_API int oidnb200_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Conv / ConcatConv (+ fused Pool, + upsampled source)   -- core/conv.h:26-61,
+ * core/concat_conv.h, core/pool.h, core/upsample.h; replaces devices/cuda/cutlass_conv.h
+ * ------------------------------------------------------------------------------------------ */
+typedef struct oidnb200_conv_desc
+{
+  int H, W;          /* resolution the convolution runs at (its un-pooled output resolution) */
+  int C1;            /* padded channels of src1 (multiple of 16) */
+  int C2;            /* padded channels of src2, 0 if the op is a plain Conv (ConcatConv otherwise) */
+  int Cout;          /* padded output channels (multiple of 16) */
+  int relu;          /* Activation::ReLU (core/conv.h:12-16) */
+  int post_op;       /* 0 none, 1 PostOp::Pool (dst is H/2 x W/2), 2 PostOp::Upsample (dst is 2H x 2W) */
+  int src1_upsampled;/* 1: src1 is stored at H/2 x W/2 and nearest-upsampled by the loader (fused Upsample) */
+  int shift_mode;    /* 0 (product). 1,2 are hardware-probe variants used only by tools/probe_conv */
+} oidnb200_conv_desc;
+
+typedef struct oidnb200_conv oidnb200_conv;
+
+OIDNB200_API int oidnb200_conv_create(const oidnb200_conv_desc* desc, oidnb200_conv** out);
+OIDNB200_API void oidnb200_conv_destroy(oidnb200_conv* conv);
+
+/* Bytes of the packed (device-layout) weight and bias buffers. */
+OIDNB200_API size_t oidnb200_conv_weight_bytes(const oidnb200_conv* conv);
+OIDNB200_API size_t oidnb200_conv_bias_bytes(const oidnb200_conv* conv);
+
+/* Host-side weight/bias reorder: TZA "oihw" fp16 [O][I][3][3] + "x" fp16 bias [O]
+ * -> packed device layout (zero padded). I = I1 + I2 logical input channels (ConcatConv splits the
+ * I axis at I1: core/graph.cpp:205-208). Stands in for reorderWeight/reorderBias
+ * (core/tensor_reorder.cpp:8-98). dst buffers are host memory of the sizes returned above. */
+OIDNB200_API int oidnb200_conv_pack_weights(const oidnb200_conv* conv, const uint16_t* w_oihw,
+                                            int O, int I1, int I2, void* dst_weights);
+OIDNB200_API int oidnb200_conv_pack_bias(const oidnb200_conv* conv, const uint16_t* b_x, int O,
+                                         void* dst_bias);
+
+/* Bind device pointers (encodes the TMA tensor maps). src2 may be NULL when C2 == 0. */
+OIDNB200_API int oidnb200_conv_bind(oidnb200_conv* conv, const void* src1, const void* src2,
+                                    const void* weights, const void* bias, void* dst);
+
+/* Conv::submitKernels (core/op.h:44-51). */
+OIDNB200_API int oidnb200_conv_launch(const oidnb200_conv* conv, oidnb200_stream stream);
+
+/* Debug/reference SIMT implementation of the same op on the same buffers (tests only). */
+OIDNB200_API int oidnb200_conv_launch_simt(const oidnb200_conv* conv, void* scratch_fp16,
+                                           oidnb200_stream stream);
+
+/* Introspection for tests / DESIGN.md numbers. */
+typedef struct oidnb200_conv_info
+{
+  int grid, smem_bytes, ngroups, cout_group, nchunks, nstages, ring_slots, rows_per_item;
+  int nstrips, nrowchunks;
+} oidnb200_conv_info;
+OIDNB200_API int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OIDN_B200_KERNELS_H */

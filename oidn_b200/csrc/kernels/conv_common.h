@@ -1,0 +1,52 @@
+// Shared host/device definitions for the 3x3 convolution kernels.
+//
+// Tensor layout in HBM (all activations): NHWC, fp16, N=1, channels padded to a multiple of 16
+// (one tcgen05 K step). The reference CUDA device uses the same "hwc" layout with blockC=8
+// (devices/cuda/cuda_device.cpp:215-219); 16 is the fp16 UMMA K granularity.
+//
+// Packed weight layout in HBM: [kw][kh][CoutAlloc][CinTot] fp16, CinTot = C1p + C2p (the padded
+// channels of src1 followed by the padded channels of src2: the in-place concat of
+// core/graph.cpp:205-208), CoutAlloc = ngroups*CoutG >= CoutPad, zero padded.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oidnb200 {
+
+constexpr int kMaxChunks   = 8;     // K chunks (<=64 channels each) over both sources
+constexpr int kMaxStages   = 8;     // A-operand pipeline depth
+constexpr int kStripW      = 128;   // output pixels per MMA tile (UMMA M)
+constexpr int kStageBytes  = 17408; // one A stage: up to 132 px x 128 B, 1024-aligned
+constexpr int kSmemHeader  = 2048;  // barriers + TMEM pointer + bias
+constexpr int kTmemCols    = 512;
+constexpr int kMaxSlots    = 32;
+constexpr int kSmemBudget  = 232448; // 227 KB opt-in dynamic shared memory per CTA
+
+enum PostOp : int { POST_NONE = 0, POST_POOL = 1, POST_UPSAMPLE = 2 };
+
+struct ConvKernelParams
+{
+  CUtensorMap amap[kMaxChunks]; // activations, one per K chunk (3D, or 4D with a stride-0 dup axis for a virtually upsampled source)
+  CUtensorMap wmap[kMaxChunks]; // packed weights, one per K chunk (4D)
+  int      nchunks;
+  int      chunk_c0[kMaxChunks];    // first channel of the chunk inside its source tensor
+  int      chunk_wc0[kMaxChunks];   // first channel of the chunk on the packed-weight Cin axis
+  int      chunk_cc[kMaxChunks];    // channels in the chunk: 16, 32 or 64 (row bytes 32/64/128)
+  int      chunk_up[kMaxChunks];    // 1: source stored at half resolution, read through the 4D dup map
+  uint32_t chunk_boff[kMaxChunks];  // byte offset of the chunk's kw=0 weight block in the B region
+  uint32_t chunk_bblk[kMaxChunks];  // bytes of one kw block (3*CoutG rows)
+  int      H, W;                    // conv resolution (= resolution of the unpooled output)
+  int      CoutG, ngroups, CoutPad; // output channels per CTA group / groups / padded total
+  int      R;                       // TMEM accumulator ring slots (R*CoutG <= 512)
+  int      RC, nstrips, nrowchunks; // rows per work item, strips across W, row chunks down H
+  int      nstages;                 // A pipeline stages
+  uint32_t w_bytes;                 // total weight bytes TMA-loaded per CTA
+  int      relu, post_op;
+  int      shift_mode;              // 0: shifted descriptor view, 1: +base_offset, 2: three kw copies (probe only)
+  void*        dst;                 // fp16 NHWC
+  int          dstC;                // channel stride of dst (padded Cout)
+  const float* bias;                // fp32 [CoutAlloc]
+};
+
+} // namespace oidnb200

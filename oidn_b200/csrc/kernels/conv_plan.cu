@@ -1,0 +1,488 @@
+// Host side of the convolution op: work decomposition, shared-memory budget, TMA tensor maps,
+// weight packing, and the C ABI (include/oidn_b200_kernels.h). Also holds the plain SIMT version
+// of the same op that the GPU tests use as a second witness.
+#include "conv_common.h"
+#include "common.h"
+#include "../../../include/oidn_b200_kernels.h"
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace oidnb200 {
+
+cudaError_t conv3x3_tc_launch(const ConvKernelParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Driver entry point for tensor-map encoding (no link-time libcuda dependency, so the library
+// still loads on a machine without a driver).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn)
+  {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int cc)
+{
+  return cc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int encode_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int cc)
+{
+  PFN_encodeTiled enc = get_encode();
+  if (!enc)
+  {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return OIDNB200_ERR_DRIVER;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i)
+  {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim,
+                   gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cc),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+  {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return OIDNB200_ERR_DRIVER;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plan
+// ------------------------------------------------------------------------------------------------
+struct ConvPlan
+{
+  oidnb200_conv_desc desc;
+  ConvKernelParams kp;
+  int grid = 0;
+  size_t smem = 0;
+  int CinTot = 0, CoutAlloc = 0;
+  int chunk_src[kMaxChunks];
+  const void *src1 = nullptr, *src2 = nullptr, *weights = nullptr;
+  bool bound = false;
+};
+
+static int num_sms()
+{
+  static int n = 0;
+  if (!n)
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    {
+      cudaGetLastError();
+      n = 148; // B200; lets the planner run (and be unit-tested) without a GPU
+    }
+  }
+  return n;
+}
+
+static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
+{
+  if (d.H <= 0 || d.W <= 0 || d.C1 <= 0 || d.C1 % 16 || d.C2 < 0 || d.C2 % 16 || d.Cout <= 0 || d.Cout % 16)
+  {
+    set_error("conv: channel counts must be positive multiples of 16 and H,W > 0");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (d.post_op == POST_POOL && ((d.H & 1) || (d.W & 1)))
+  {
+    set_error("conv: PostOp::Pool needs even H and W");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (d.src1_upsampled && ((d.H & 1) || (d.W & 1)))
+  {
+    set_error("conv: upsampled source needs even H and W");
+    return OIDNB200_ERR_INVALID;
+  }
+  pl.desc = d;
+  ConvKernelParams& kp = pl.kp;
+  memset(&kp, 0, sizeof(kp));
+
+  // K chunks: each source is cut into 64/32/16-channel pieces (row bytes 128/64/32).
+  int n = 0;
+  const int Cs[2] = {d.C1, d.C2};
+  int wc0 = 0;
+  for (int s = 0; s < 2; ++s)
+  {
+    int c0 = 0, rem = Cs[s];
+    while (rem > 0)
+    {
+      const int cc = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+      if (n >= kMaxChunks)
+      {
+        set_error("conv: too many K chunks");
+        return OIDNB200_ERR_UNSUPPORTED;
+      }
+      kp.chunk_c0[n] = c0;
+      kp.chunk_wc0[n] = wc0;
+      kp.chunk_cc[n] = cc;
+      kp.chunk_up[n] = (s == 0 && d.src1_upsampled) ? 1 : 0;
+      pl.chunk_src[n] = s;
+      c0 += cc; wc0 += cc; rem -= cc; ++n;
+    }
+  }
+  kp.nchunks = n;
+  pl.CinTot = d.C1 + d.C2;
+
+  // Output-channel group: the largest one whose resident weights leave room for >= 3 A stages.
+  const uint32_t stage_bytes = (d.shift_mode == 2) ? 3u * 16384u : (uint32_t)kStageBytes;
+  const int min_stages = (d.shift_mode == 2) ? 2 : 3;
+  const uint32_t avail = kSmemBudget - 1024 /*alignment slack*/ - kSmemHeader;
+  auto b_bytes = [&](int CoutG) {
+    uint32_t off = 0;
+    for (int c = 0; c < n; ++c)
+      off = align_up(off, 1024) + 3u * (3u * CoutG * kp.chunk_cc[c] * 2u);
+    return off;
+  };
+  int CoutG = std::min(d.Cout, 128);
+  while (CoutG > 16 && b_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
+  if (b_bytes(CoutG) + min_stages * stage_bytes > avail)
+  {
+    set_error("conv: weights for 16 output channels do not fit in shared memory");
+    return OIDNB200_ERR_UNSUPPORTED;
+  }
+  const int ngroups = (d.Cout + CoutG - 1) / CoutG;
+  CoutG = ((d.Cout + ngroups - 1) / ngroups + 15) / 16 * 16; // rebalance
+  kp.CoutG = CoutG;
+  kp.ngroups = ngroups;
+  kp.CoutPad = d.Cout;
+  pl.CoutAlloc = CoutG * ngroups;
+  kp.R = std::min(kMaxSlots, kTmemCols / CoutG);
+
+  uint32_t off = 0;
+  for (int c = 0; c < n; ++c)
+  {
+    off = align_up(off, 1024);
+    kp.chunk_boff[c] = off;
+    kp.chunk_bblk[c] = 3u * CoutG * kp.chunk_cc[c] * 2u;
+    off += 3u * kp.chunk_bblk[c];
+  }
+  const uint32_t bbytes = off;
+  kp.w_bytes = 9u * CoutG * pl.CinTot * 2u;
+  int nstages = (int)((avail - bbytes) / stage_bytes);
+  nstages = std::min(nstages, kMaxStages);
+  kp.nstages = nstages;
+  pl.smem = 1024 + kSmemHeader + (size_t)nstages * stage_bytes + bbytes;
+
+  // Work decomposition: strips of 128 px x RC rows; pick RC minimising the critical path.
+  kp.H = d.H; kp.W = d.W;
+  kp.nstrips = (d.W + kStripW - 1) / kStripW;
+  const int P = std::max(1, num_sms() / ngroups);
+  const int step = (d.post_op == POST_POOL) ? 2 : 1;
+  int bestRC = step;
+  long bestCost = -1;
+  for (int RC = step; RC <= d.H + step - 1; RC += step)
+  {
+    const long items = (long)kp.nstrips * ((d.H + RC - 1) / RC);
+    const long waves = (items + P - 1) / P;
+    const long cost = waves * (RC + 2);
+    if (bestCost < 0 || cost < bestCost || (cost == bestCost && RC > bestRC))
+    {
+      bestCost = cost;
+      bestRC = RC;
+    }
+  }
+  kp.RC = bestRC;
+  kp.nrowchunks = (d.H + bestRC - 1) / bestRC;
+  const int items = kp.nstrips * kp.nrowchunks;
+  pl.grid = std::min(P, items) * ngroups;
+
+  kp.relu = d.relu;
+  kp.post_op = d.post_op;
+  kp.shift_mode = d.shift_mode;
+  kp.dstC = d.Cout;
+  return 0;
+}
+
+static int plan_bind(ConvPlan& pl, const void* src1, const void* src2, const void* weights,
+                     const void* bias, void* dst)
+{
+  const oidnb200_conv_desc& d = pl.desc;
+  ConvKernelParams& kp = pl.kp;
+  if (!src1 || (d.C2 > 0 && !src2) || !weights || !bias || !dst)
+  {
+    set_error("conv: null pointer in bind");
+    return OIDNB200_ERR_INVALID;
+  }
+  for (int c = 0; c < kp.nchunks; ++c)
+  {
+    const int s = pl.chunk_src[c];
+    const int C = s == 0 ? d.C1 : d.C2;
+    const void* base = s == 0 ? src1 : src2;
+    const int cc = kp.chunk_cc[c];
+    int rc;
+    if (kp.chunk_up[c])
+    {
+      const uint64_t Wl = d.W / 2, Hl = d.H / 2;
+      const uint64_t dims[4] = {(uint64_t)C, 2, Wl, Hl};
+      const uint64_t str[3] = {0, (uint64_t)C * 2, Wl * C * 2};
+      const uint32_t box[4] = {(uint32_t)cc, 2, 66, 1};
+      rc = encode_tmap(&kp.amap[c], base, 4, dims, str, box, cc);
+    }
+    else
+    {
+      const uint64_t dims[3] = {(uint64_t)C, (uint64_t)d.W, (uint64_t)d.H};
+      const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)d.W * C * 2};
+      const uint32_t box[3] = {(uint32_t)cc, d.shift_mode == 2 ? 128u : 130u, 1};
+      rc = encode_tmap(&kp.amap[c], base, 3, dims, str, box, cc);
+    }
+    if (rc) return rc;
+    const uint64_t wd[4] = {(uint64_t)pl.CinTot, (uint64_t)pl.CoutAlloc, 3, 3};
+    const uint64_t ws[3] = {(uint64_t)pl.CinTot * 2, (uint64_t)pl.CoutAlloc * pl.CinTot * 2,
+                            (uint64_t)3 * pl.CoutAlloc * pl.CinTot * 2};
+    const uint32_t wb[4] = {(uint32_t)cc, (uint32_t)kp.CoutG, 3, 1};
+    rc = encode_tmap(&kp.wmap[c], weights, 4, wd, ws, wb, cc);
+    if (rc) return rc;
+  }
+  kp.dst = dst;
+  kp.bias = static_cast<const float*>(bias);
+  pl.src1 = src1; pl.src2 = src2; pl.weights = weights;
+  pl.bound = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT witness: one thread per (pixel, output channel), fp32 accumulation in kh,kw,ci order.
+// ------------------------------------------------------------------------------------------------
+__global__ void conv3x3_simt_kernel(const __half* __restrict__ src1, const __half* __restrict__ src2,
+                                    int C1, int C2, int up1, int H, int W,
+                                    const __half* __restrict__ wts, int CinTot, int CoutAlloc,
+                                    const float* __restrict__ bias, int Cout, int relu,
+                                    __half* __restrict__ out /* [H][W][Cout] */)
+{
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)H * W * Cout) return;
+  const int co = (int)(idx % Cout);
+  const int x = (int)((idx / Cout) % W);
+  const int y = (int)(idx / ((long)Cout * W));
+  float acc = bias[co];
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw)
+    {
+      const int yy = y + kh - 1, xx = x + kw - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __half* w = wts + ((size_t)(kw * 3 + kh) * CoutAlloc + co) * CinTot;
+      const __half* s1 = up1 ? src1 + ((size_t)(yy >> 1) * (W >> 1) + (xx >> 1)) * C1
+                             : src1 + ((size_t)yy * W + xx) * C1;
+      for (int ci = 0; ci < C1; ++ci) acc += __half2float(w[ci]) * __half2float(s1[ci]);
+      if (C2 > 0)
+      {
+        const __half* s2 = src2 + ((size_t)yy * W + xx) * C2;
+        for (int ci = 0; ci < C2; ++ci) acc += __half2float(w[C1 + ci]) * __half2float(s2[ci]);
+      }
+    }
+  if (relu) acc = fmaxf(acc, 0.f);
+  out[idx] = __float2half_rn(acc);
+}
+
+__global__ void post_simt_kernel(const __half* __restrict__ in, int H, int W, int C, int post_op,
+                                 __half* __restrict__ dst)
+{
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (post_op == POST_POOL)
+  {
+    const int Ho = H / 2, Wo = W / 2;
+    if (idx >= (long)Ho * Wo * C) return;
+    const int c = (int)(idx % C);
+    const int x = (int)((idx / C) % Wo);
+    const int y = (int)(idx / ((long)C * Wo));
+    float m = -INFINITY;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx)
+        m = fmaxf(m, __half2float(in[((size_t)(2 * y + dy) * W + 2 * x + dx) * C + c]));
+    dst[idx] = __float2half_rn(m);
+  }
+  else if (post_op == POST_UPSAMPLE)
+  {
+    const int Ho = H * 2, Wo = W * 2;
+    if (idx >= (long)Ho * Wo * C) return;
+    const int c = (int)(idx % C);
+    const int x = (int)((idx / C) % Wo);
+    const int y = (int)(idx / ((long)C * Wo));
+    dst[idx] = in[((size_t)(y >> 1) * W + (x >> 1)) * C + c];
+  }
+  else
+  {
+    if (idx >= (long)H * W * C) return;
+    dst[idx] = in[idx];
+  }
+}
+
+} // namespace oidnb200
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace oidnb200;
+
+struct oidnb200_conv
+{
+  ConvPlan plan;
+};
+
+extern "C" {
+
+int oidnb200_conv_create(const oidnb200_conv_desc* desc, oidnb200_conv** out)
+{
+  if (!desc || !out)
+  {
+    set_error("conv_create: null argument");
+    return OIDNB200_ERR_INVALID;
+  }
+  oidnb200_conv* c = new oidnb200_conv();
+  const int rc = plan_create(*desc, c->plan);
+  if (rc)
+  {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+void oidnb200_conv_destroy(oidnb200_conv* conv) { delete conv; }
+
+size_t oidnb200_conv_weight_bytes(const oidnb200_conv* conv)
+{
+  return (size_t)9 * conv->plan.CoutAlloc * conv->plan.CinTot * sizeof(uint16_t);
+}
+
+size_t oidnb200_conv_bias_bytes(const oidnb200_conv* conv)
+{
+  return (size_t)conv->plan.CoutAlloc * sizeof(float);
+}
+
+int oidnb200_conv_pack_weights(const oidnb200_conv* conv, const uint16_t* w_oihw, int O, int I1, int I2,
+                               void* dst_weights)
+{
+  const ConvPlan& pl = conv->plan;
+  if (!w_oihw || !dst_weights || O > pl.desc.Cout || I1 > pl.desc.C1 || I2 > pl.desc.C2 || O <= 0 || I1 <= 0 || I2 < 0)
+  {
+    set_error("conv_pack_weights: logical dims exceed padded dims");
+    return OIDNB200_ERR_INVALID;
+  }
+  uint16_t* dst = static_cast<uint16_t*>(dst_weights);
+  memset(dst, 0, oidnb200_conv_weight_bytes(conv));
+  const int I = I1 + I2;
+  for (int o = 0; o < O; ++o)
+    for (int i = 0; i < I; ++i)
+    {
+      const int ci = i < I1 ? i : pl.desc.C1 + (i - I1); // src2 channels follow src1's padded ones
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          dst[((size_t)(kw * 3 + kh) * pl.CoutAlloc + o) * pl.CinTot + ci] =
+            w_oihw[(((size_t)o * I + i) * 3 + kh) * 3 + kw];
+    }
+  return 0;
+}
+
+int oidnb200_conv_pack_bias(const oidnb200_conv* conv, const uint16_t* b_x, int O, void* dst_bias)
+{
+  const ConvPlan& pl = conv->plan;
+  if (!b_x || !dst_bias || O > pl.desc.Cout || O <= 0)
+  {
+    set_error("conv_pack_bias: bad arguments");
+    return OIDNB200_ERR_INVALID;
+  }
+  float* dst = static_cast<float*>(dst_bias);
+  for (int o = 0; o < pl.CoutAlloc; ++o) dst[o] = o < O ? half_bits_to_float(b_x[o]) : 0.f;
+  return 0;
+}
+
+int oidnb200_conv_bind(oidnb200_conv* conv, const void* src1, const void* src2, const void* weights,
+                       const void* bias, void* dst)
+{
+  return plan_bind(conv->plan, src1, src2, weights, bias, dst);
+}
+
+int oidnb200_conv_launch(const oidnb200_conv* conv, oidnb200_stream stream)
+{
+  const ConvPlan& pl = conv->plan;
+  if (!pl.bound)
+  {
+    set_error("conv_launch: op not bound");
+    return OIDNB200_ERR_INVALID;
+  }
+  cudaError_t e = conv3x3_tc_launch(pl.kp, pl.grid, pl.smem, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+  {
+    set_error(std::string("conv_launch: ") + cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int oidnb200_conv_launch_simt(const oidnb200_conv* conv, void* scratch, oidnb200_stream stream)
+{
+  const ConvPlan& pl = conv->plan;
+  const oidnb200_conv_desc& d = pl.desc;
+  if (!pl.bound || !scratch)
+  {
+    set_error("conv_launch_simt: op not bound or no scratch");
+    return OIDNB200_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long n = (long)d.H * d.W * d.Cout;
+  conv3x3_simt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+    static_cast<const __half*>(pl.src1), static_cast<const __half*>(pl.src2), d.C1, d.C2,
+    d.src1_upsampled, d.H, d.W, static_cast<const __half*>(pl.weights), pl.CinTot, pl.CoutAlloc,
+    pl.kp.bias, d.Cout, d.relu, static_cast<__half*>(scratch));
+  long m = n;
+  if (d.post_op == POST_POOL) m = n / 4;
+  if (d.post_op == POST_UPSAMPLE) m = n * 4;
+  post_simt_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(static_cast<const __half*>(scratch), d.H,
+                                                               d.W, d.Cout, d.post_op,
+                                                               static_cast<__half*>(pl.kp.dst));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+  {
+    set_error(std::string("conv_launch_simt: ") + cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info)
+{
+  const ConvPlan& pl = conv->plan;
+  info->grid = pl.grid;
+  info->smem_bytes = (int)pl.smem;
+  info->ngroups = pl.kp.ngroups;
+  info->cout_group = pl.kp.CoutG;
+  info->nchunks = pl.kp.nchunks;
+  info->nstages = pl.kp.nstages;
+  info->ring_slots = pl.kp.R;
+  info->rows_per_item = pl.kp.RC;
+  info->nstrips = pl.kp.nstrips;
+  info->nrowchunks = pl.kp.nrowchunks;
+  return 0;
+}
+
+} // extern "C"
