@@ -15,6 +15,7 @@
 namespace oidnb200 {
 
 constexpr int kMaxChunks   = 8;     // K chunks (<=64 channels each) over both sources
+constexpr int kMaxOutChunks = 3;    // output-channel pieces (64/32/16) of one CoutG group
 constexpr int kMaxStages   = 8;     // A-operand pipeline depth
 constexpr int kStripW      = 128;   // output pixels per MMA tile (UMMA M)
 constexpr int kStageBytes  = 17408; // one A stage: up to 132 px x 128 B, 1024-aligned
@@ -23,12 +24,13 @@ constexpr int kTmemCols    = 512;
 constexpr int kMaxSlots    = 32;
 constexpr int kSmemBudget  = 232448; // 227 KB opt-in dynamic shared memory per CTA
 
-enum PostOp : int { POST_NONE = 0, POST_POOL = 1, POST_UPSAMPLE = 2 };
+enum PostOp : int { POST_NONE = 0, POST_POOL = 1, POST_UPSAMPLE = 2 /* SIMT witness only */ };
 
 struct ConvKernelParams
 {
   CUtensorMap amap[kMaxChunks]; // activations, one per K chunk (3D, or 4D with a stride-0 dup axis for a virtually upsampled source)
   CUtensorMap wmap[kMaxChunks]; // packed weights, one per K chunk (4D)
+  CUtensorMap omap[kMaxOutChunks]; // destination, one per output-channel piece of the group (3D)
   int      nchunks;
   int      chunk_c0[kMaxChunks];    // first channel of the chunk inside its source tensor
   int      chunk_wc0[kMaxChunks];   // first channel of the chunk on the packed-weight Cin axis
@@ -42,10 +44,14 @@ struct ConvKernelParams
   int      RC, nstrips, nrowchunks; // rows per work item, strips across W, row chunks down H
   int      nstages;                 // A pipeline stages
   uint32_t w_bytes;                 // total weight bytes TMA-loaded per CTA
+  uint32_t b_bytes;                 // size of the resident weight region (1024-aligned blocks)
+  int      nout;                    // output pieces of the group
+  int      out_c0[kMaxOutChunks];   // first channel of the piece inside the group
+  int      out_cc[kMaxOutChunks];   // channels in the piece (64/32/16)
+  uint32_t out_off[kMaxOutChunks];  // byte offset of the piece inside one staging buffer
+  uint32_t out_buf_bytes;           // bytes of one staging buffer
+  int      out_nbuf;                // 1 or 2 staging buffers
   int      relu, post_op;
-  int      shift_mode;              // 0: shifted descriptor view, 1: +base_offset, 2: three kw copies (probe only)
-  void*        dst;                 // fp16 NHWC
-  int          dstC;                // channel stride of dst (padded Cout)
   const float* bias;                // fp32 [CoutAlloc]
 };
 

@@ -83,6 +83,7 @@ struct ConvPlan
   int CinTot = 0, CoutAlloc = 0;
   int chunk_src[kMaxChunks];
   const void *src1 = nullptr, *src2 = nullptr, *weights = nullptr;
+  void* dst = nullptr;
   bool bound = false;
 };
 
@@ -114,6 +115,11 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   if (d.post_op == POST_POOL && ((d.H & 1) || (d.W & 1)))
   {
     set_error("conv: PostOp::Pool needs even H and W");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (d.shift_mode != 0)
+  {
+    set_error("conv: shift_mode 1/2 were hardware-probe variants (profiles/probe_r01.md); only 0 exists");
     return OIDNB200_ERR_INVALID;
   }
   if (d.src1_upsampled && ((d.H & 1) || (d.W & 1)))
@@ -151,19 +157,31 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   kp.nchunks = n;
   pl.CinTot = d.C1 + d.C2;
 
-  // Output-channel group: the largest one whose resident weights leave room for >= 3 A stages.
-  const uint32_t stage_bytes = (d.shift_mode == 2) ? 3u * 16384u : (uint32_t)kStageBytes;
-  const int min_stages = (d.shift_mode == 2) ? 2 : 3;
+  // Output-channel group: the largest one whose resident weights + output staging leave room for
+  // at least two A stages.
+  const uint32_t stage_bytes = (uint32_t)kStageBytes;
+  const int min_stages = 2;
   const uint32_t avail = kSmemBudget - 1024 /*alignment slack*/ - kSmemHeader;
   auto b_bytes = [&](int CoutG) {
     uint32_t off = 0;
     for (int c = 0; c < n; ++c)
       off = align_up(off, 1024) + 3u * (3u * CoutG * kp.chunk_cc[c] * 2u);
-    return off;
+    return align_up(off, 1024);
+  };
+  const uint32_t out_px = (d.post_op == POST_POOL) ? 64u : 128u;
+  auto out_bytes = [&](int CoutG) { // one staging buffer: pieces of 64/32/16 channels, 1024-aligned
+    uint32_t off = 0;
+    for (int rem = CoutG; rem > 0;)
+    {
+      const int cc = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+      off = align_up(off, 1024) + out_px * cc * 2u;
+      rem -= cc;
+    }
+    return align_up(off, 1024);
   };
   int CoutG = std::min(d.Cout, 128);
-  while (CoutG > 16 && b_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
-  if (b_bytes(CoutG) + min_stages * stage_bytes > avail)
+  while (CoutG > 16 && b_bytes(CoutG) + out_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
+  if (b_bytes(CoutG) + out_bytes(CoutG) + min_stages * stage_bytes > avail)
   {
     set_error("conv: weights for 16 output channels do not fit in shared memory");
     return OIDNB200_ERR_UNSUPPORTED;
@@ -184,12 +202,33 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
     kp.chunk_bblk[c] = 3u * CoutG * kp.chunk_cc[c] * 2u;
     off += 3u * kp.chunk_bblk[c];
   }
-  const uint32_t bbytes = off;
+  const uint32_t bbytes = align_up(off, 1024);
+  kp.b_bytes = bbytes;
   kp.w_bytes = 9u * CoutG * pl.CinTot * 2u;
-  int nstages = (int)((avail - bbytes) / stage_bytes);
-  nstages = std::min(nstages, kMaxStages);
+
+  // output pieces
+  kp.nout = 0;
+  uint32_t ooff = 0;
+  for (int c0 = 0, rem = CoutG; rem > 0;)
+  {
+    const int cc = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+    ooff = align_up(ooff, 1024);
+    kp.out_c0[kp.nout] = c0;
+    kp.out_cc[kp.nout] = cc;
+    kp.out_off[kp.nout] = ooff;
+    ooff += out_px * cc * 2u;
+    c0 += cc; rem -= cc; kp.nout++;
+  }
+  kp.out_buf_bytes = align_up(ooff, 1024);
+
+  // split what is left between a second staging buffer and A stages (>= 3 stages before double
+  // buffering the output)
+  uint32_t left = avail - bbytes - kp.out_buf_bytes;
+  kp.out_nbuf = (left >= kp.out_buf_bytes + 3 * stage_bytes) ? 2 : 1;
+  if (kp.out_nbuf == 2) left -= kp.out_buf_bytes;
+  int nstages = std::min((int)(left / stage_bytes), kMaxStages);
   kp.nstages = nstages;
-  pl.smem = 1024 + kSmemHeader + (size_t)nstages * stage_bytes + bbytes;
+  pl.smem = 1024 + kSmemHeader + (size_t)nstages * stage_bytes + bbytes + (size_t)kp.out_nbuf * kp.out_buf_bytes;
 
   // Work decomposition: strips of 128 px x RC rows; pick RC minimising the critical path.
   kp.H = d.H; kp.W = d.W;
@@ -216,8 +255,6 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
 
   kp.relu = d.relu;
   kp.post_op = d.post_op;
-  kp.shift_mode = d.shift_mode;
-  kp.dstC = d.Cout;
   return 0;
 }
 
@@ -250,7 +287,7 @@ static int plan_bind(ConvPlan& pl, const void* src1, const void* src2, const voi
     {
       const uint64_t dims[3] = {(uint64_t)C, (uint64_t)d.W, (uint64_t)d.H};
       const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)d.W * C * 2};
-      const uint32_t box[3] = {(uint32_t)cc, d.shift_mode == 2 ? 128u : 130u, 1};
+      const uint32_t box[3] = {(uint32_t)cc, 130u, 1};
       rc = encode_tmap(&kp.amap[c], base, 3, dims, str, box, cc);
     }
     if (rc) return rc;
@@ -261,7 +298,18 @@ static int plan_bind(ConvPlan& pl, const void* src1, const void* src2, const voi
     rc = encode_tmap(&kp.wmap[c], weights, 4, wd, ws, wb, cc);
     if (rc) return rc;
   }
-  kp.dst = dst;
+  {
+    const uint64_t Wd = d.post_op == POST_POOL ? d.W / 2 : d.W, Hd = d.post_op == POST_POOL ? d.H / 2 : d.H;
+    const uint64_t od[3] = {(uint64_t)d.Cout, Wd, Hd};
+    const uint64_t os[2] = {(uint64_t)d.Cout * 2, Wd * d.Cout * 2};
+    for (int oc = 0; oc < kp.nout; ++oc)
+    {
+      const uint32_t ob[3] = {(uint32_t)kp.out_cc[oc], d.post_op == POST_POOL ? 64u : 128u, 1};
+      const int rc = encode_tmap(&kp.omap[oc], dst, 3, od, os, ob, kp.out_cc[oc]);
+      if (rc) return rc;
+    }
+  }
+  pl.dst = dst;
   kp.bias = static_cast<const float*>(bias);
   pl.src1 = src1; pl.src2 = src2; pl.weights = weights;
   pl.bound = true;
@@ -430,6 +478,12 @@ int oidnb200_conv_launch(const oidnb200_conv* conv, oidnb200_stream stream)
     set_error("conv_launch: op not bound");
     return OIDNB200_ERR_INVALID;
   }
+  if (pl.desc.post_op == POST_UPSAMPLE)
+  {
+    set_error("conv_launch: PostOp::Upsample is fused into the consumer (src1_upsampled); "
+              "the tensor-core kernel never materialises an upsampled tensor");
+    return OIDNB200_ERR_UNSUPPORTED;
+  }
   cudaError_t e = conv3x3_tc_launch(pl.kp, pl.grid, pl.smem, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess)
   {
@@ -459,7 +513,7 @@ int oidnb200_conv_launch_simt(const oidnb200_conv* conv, void* scratch, oidnb200
   if (d.post_op == POST_UPSAMPLE) m = n * 4;
   post_simt_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(static_cast<const __half*>(scratch), d.H,
                                                                d.W, d.Cout, d.post_op,
-                                                               static_cast<__half*>(pl.kp.dst));
+                                                               static_cast<__half*>(pl.dst));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
   {

@@ -86,7 +86,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   const int nitems  = p.nstrips * p.nrowchunks;
   const int NS      = p.nstages;
   const int R       = p.R;
-  const uint32_t stage_bytes = (p.shift_mode == 2) ? 3u * 16384u : (uint32_t)kStageBytes;
+  const uint32_t stage_bytes = (uint32_t)kStageBytes;
   const uint32_t b_region = sbase + SmemLayout::a_ring + NS * stage_bytes;
 
   // ---------------------------------------------------------------- setup
@@ -127,31 +127,34 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + SmemLayout::tmem_ptr);
 
   // ---------------------------------------------------------------- TMA producer
+  // Both single-issuer roles keep warp-uniform control flow (all 32 lanes walk the loops, one
+  // elected lane issues): values stay in uniform registers instead of being broadcast per use.
   if (warp == 0)
   {
-    if (lane == 0)
+    const bool leader = elect_one();
+    // Resident weights of this CTA's output-channel group: [kw][chunk] blocks of 3*CoutG rows.
+    if (leader)
     {
-      // Resident weights of this CTA's output-channel group: [kw][chunk] blocks of 3*CoutG rows.
       mbar_arrive_expect_tx(sbase + SmemLayout::w_full, p.w_bytes);
       for (int c = 0; c < p.nchunks; ++c)
         for (int kw = 0; kw < 3; ++kw)
           tma_load_4d(b_region + p.chunk_boff[c] + kw * p.chunk_bblk[c], &p.wmap[c],
                       sbase + SmemLayout::w_full, p.chunk_wc0[c], group * p.CoutG, 0, kw);
-
-      uint32_t k = 0;
-      for (int item = cta; item < nitems; item += nctas)
+    }
+    uint32_t s = 0, ph = 0;
+    for (int item = cta; item < nitems; item += nctas)
+    {
+      const Item it = get_item(p, item);
+      for (int r = it.y0 - 1; r <= it.y1 + 1; ++r)
       {
-        const Item it = get_item(p, item);
-        for (int r = it.y0 - 1; r <= it.y1 + 1; ++r)
+        for (int c = 0; c < p.nchunks; ++c)
         {
-          for (int c = 0; c < p.nchunks; ++c, ++k)
+          const uint32_t full = sbase + SmemLayout::full_a + 8 * s;
+          const uint32_t dst  = sbase + SmemLayout::a_ring + s * stage_bytes;
+          mbar_wait(sbase + SmemLayout::empty_a + 8 * s, ph ^ 1, 1);
+          const int cc = p.chunk_cc[c];
+          if (leader)
           {
-            const uint32_t s  = k % NS;
-            const uint32_t ph = (k / NS) & 1;
-            const uint32_t full = sbase + SmemLayout::full_a + 8 * s;
-            const uint32_t dst  = sbase + SmemLayout::a_ring + s * stage_bytes;
-            mbar_wait(sbase + SmemLayout::empty_a + 8 * s, ph ^ 1, 1);
-            const int cc = p.chunk_cc[c];
             if (p.chunk_up[c])
             {
               // 132 virtual pixels starting at x0-2: (dup 2, stride 0) x (66 half-res pixels);
@@ -160,18 +163,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
               mbar_arrive_expect_tx(full, 132u * cc * 2u);
               tma_load_4d(dst, &p.amap[c], full, p.chunk_c0[c], 0, it.x0 / 2 - 1, r >> 1);
             }
-            else if (p.shift_mode == 2)
-            {
-              mbar_arrive_expect_tx(full, 3u * 128u * cc * 2u);
-              for (int kw = 0; kw < 3; ++kw)
-                tma_load_3d(dst + kw * 16384u, &p.amap[c], full, p.chunk_c0[c], it.x0 - 1 + kw, r);
-            }
             else
             {
               mbar_arrive_expect_tx(full, 130u * cc * 2u);
               tma_load_3d(dst, &p.amap[c], full, p.chunk_c0[c], it.x0 - 1, r);
             }
           }
+          if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -180,197 +178,216 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   // ---------------------------------------------------------------- MMA issuer
   else if (warp == 1)
   {
-    if (lane == 0)
+    // One lane issues every tcgen05.mma of the CTA, so this loop must cost only a handful of
+    // instructions per MMA: descriptors are (constant high word | running low word), ring/slot
+    // arithmetic is hoisted to once per input row, and there are at most two runs per row.
+    const bool leader = elect_one();
+    mbar_wait(sbase + SmemLayout::w_full, 0, 2);
+    tc_fence_after();
+    const uint32_t CoutG = p.CoutG;
+    const uint32_t max_run = min(3u, 256u / CoutG);
+    const uint32_t idesc1 = umma_idesc_f16(CoutG);
+    uint32_t stage = 0, sphase = 0;       // A ring position / parity
+    uint32_t a_mod = 0, a_par = 0;        // (first accumulator index of the item) % R, parity of / R
+    for (int item = cta; item < nitems; item += nctas)
     {
-      mbar_wait(sbase + SmemLayout::w_full, 0, 2);
-      tc_fence_after();
-      const int CoutG = p.CoutG;
-      const int max_run = min(3, 256 / CoutG);
-      uint32_t k = 0;
-      uint32_t accbase = 0;
-      for (int item = cta; item < nitems; item += nctas)
+      const Item it = get_item(p, item);
+      uint32_t top_mod = a_mod, top_par = a_par; // accumulator fed by kh=0 of the current row
+      for (int r = it.y0 - 1; r <= it.y1 + 1; ++r)
       {
-        const Item it = get_item(p, item);
-        for (int r = it.y0 - 1; r <= it.y1 + 1; ++r)
+        // Input row r feeds output row y = r - kh + 1 for every kh with y inside the item.
+        const int kh_lo = max(0, r + 1 - it.y1);
+        const int kh_hi = min(2, r + 1 - it.y0);
+        const bool fresh = (kh_lo == 0);
+        if (fresh)
         {
-          // Input row r feeds output row y = r - kh + 1 for every kh with y inside the item.
-          const int kh_lo = max(0, r + 1 - it.y1);
-          const int kh_hi = min(2, r + 1 - it.y0);
-          const uint32_t a_top = accbase + (uint32_t)(r + 1 - it.y0); // accumulator index of kh=0
-          if (kh_lo == 0)
+          // kh=0 opens a fresh accumulator: its ring slot must have been drained.
+          mbar_wait(sbase + SmemLayout::tmem_empty + 8 * ((R - 1) - top_mod), top_par ^ 1, 3);
+          tc_fence_after();
+        }
+        // Split kh_lo..kh_hi into (at most two) runs contiguous in TMEM (ring wrap) with N <= 256.
+        uint32_t d0 = 0, n0 = 0, brow0 = 0, d1 = 0, n1 = 0, brow1 = 0;
+        for (int kh = kh_lo; kh <= kh_hi; ++kh)
+        {
+          int m = (int)top_mod - kh;
+          if (m < 0) m += R;
+          const uint32_t slot = (R - 1) - m;
+          if (n0 == 0)
           {
-            // kh=0 opens a fresh accumulator: its ring slot must have been drained.
-            const uint32_t slot = (R - 1) - (a_top % R);
-            mbar_wait(sbase + SmemLayout::tmem_empty + 8 * slot, ((a_top / R) & 1) ^ 1, 3);
-            tc_fence_after();
+            d0 = tmem_base + slot * CoutG; brow0 = kh * CoutG; n0 = 1;
           }
-          // Split kh_lo..kh_hi into runs that are contiguous in TMEM (ring wrap) and N <= 256.
-          int run_kh[3], run_n[3], nruns = 0;
-          for (int kh = kh_lo; kh <= kh_hi; ++kh)
+          else if (n1 == 0 && slot != 0 && n0 < max_run)
+            n0++;
+          else if (n1 == 0)
           {
-            const uint32_t slot = (R - 1) - ((a_top - kh) % R);
-            if (nruns > 0 && slot != 0 && run_n[nruns - 1] < max_run)
-              run_n[nruns - 1]++;
-            else
+            d1 = tmem_base + slot * CoutG; brow1 = kh * CoutG; n1 = 1;
+          }
+          else
+            n1++;
+        }
+        const uint32_t idesc_r0 = umma_idesc_f16(n0 * CoutG);
+        const uint32_t idesc_r1 = umma_idesc_f16(n1 * CoutG);
+
+        for (int c = 0; c < p.nchunks; ++c)
+        {
+          mbar_wait(sbase + SmemLayout::full_a + 8 * stage, sphase, 4);
+          tc_fence_after();
+          const uint32_t cc     = p.chunk_cc[c];
+          const uint32_t row16  = cc >> 3;                      // row bytes / 16
+          const uint32_t hi     = (uint32_t)(umma_desc(0, cc * 2, 0) >> 32); // SBO, version, swizzle
+          const uint32_t a_base = sbase + SmemLayout::a_ring + stage * stage_bytes
+                                  + (p.chunk_up[c] ? cc * 2 : 0); // upsampled rows start at x0-2
+          const uint32_t a_lo0  = (a_base & 0x3FFFFu) >> 4;
+          const uint32_t b_lo0  = ((b_region + p.chunk_boff[c]) & 0x3FFFFu) >> 4;
+          const uint32_t bblk16 = p.chunk_bblk[c] >> 4;
+          const uint32_t rb0 = brow0 * row16, rb1 = brow1 * row16;
+          const uint32_t nk = cc >> 4;
+          uint32_t j0 = 0;
+          if (fresh && c == 0)
+          {
+            // the first contribution to the fresh accumulator (kh=0 block of run 0) overwrites it
+            if (leader)
             {
-              run_kh[nruns] = kh;
-              run_n[nruns]  = 1;
-              nruns++;
+              umma_f16(d0, make_desc(hi, a_lo0), make_desc(hi, b_lo0 + rb0), idesc1, 0u);
+              if (n0 > 1)
+                umma_f16(d0 + CoutG, make_desc(hi, a_lo0), make_desc(hi, b_lo0 + rb0 + CoutG * row16),
+                         umma_idesc_f16((n0 - 1) * CoutG), 1u);
+              if (n1)
+                umma_f16(d1, make_desc(hi, a_lo0), make_desc(hi, b_lo0 + rb1), idesc_r1, 1u);
             }
+            j0 = 1;
           }
-          for (int c = 0; c < p.nchunks; ++c, ++k)
+          for (uint32_t kw = 0; kw < 3; ++kw)
           {
-            const uint32_t s  = k % NS;
-            const uint32_t ph = (k / NS) & 1;
-            mbar_wait(sbase + SmemLayout::full_a + 8 * s, ph, 4);
-            tc_fence_after();
-            const uint32_t cc = p.chunk_cc[c];
-            const uint32_t row_bytes = cc * 2;
-            const uint32_t a_stage = sbase + SmemLayout::a_ring + s * stage_bytes;
-            const uint32_t px_off  = p.chunk_up[c] ? 1u : 0u; // upsampled rows start at x0-2
-            for (int kw = 0; kw < 3; ++kw)
+            const uint32_t a_kw = a_lo0 + kw * row16;
+            const uint32_t b_kw = b_lo0 + kw * bblk16;
+            for (uint32_t j = (kw == 0 ? j0 : 0u); j < nk; ++j)
             {
-              const uint32_t a_tap = (p.shift_mode == 2 && !p.chunk_up[c])
-                                       ? a_stage + kw * 16384u
-                                       : a_stage + (kw + px_off) * row_bytes;
-              const uint32_t b_tap = b_region + p.chunk_boff[c] + kw * p.chunk_bblk[c];
-              for (uint32_t j = 0; j < cc / 16; ++j)
+              if (leader)
               {
-                const uint32_t a_addr = a_tap + j * 32;
-                const uint32_t a_bo   = (p.shift_mode == 1) ? ((a_addr >> 7) & 7u) : 0u;
-                const uint64_t adesc  = umma_desc(a_addr, row_bytes, a_bo);
-                const bool first = (c == 0 && kw == 0 && j == 0);
-                for (int q = 0; q < nruns; ++q)
-                {
-                  int kh = run_kh[q], n = run_n[q];
-                  const uint32_t slot = (R - 1) - ((a_top - kh) % R);
-                  uint32_t d_addr = tmem_base + slot * CoutG;
-                  uint32_t b_addr = b_tap + kh * CoutG * row_bytes + j * 32;
-                  if (first && kh == 0)
-                  {
-                    // first contribution to the fresh accumulator overwrites it
-                    umma_f16(d_addr, adesc, umma_desc(b_addr, row_bytes, 0),
-                             umma_idesc_f16(CoutG), 0u);
-                    kh++; n--;
-                    d_addr += CoutG;
-                    b_addr += CoutG * row_bytes;
-                  }
-                  if (n > 0)
-                    umma_f16(d_addr, adesc, umma_desc(b_addr, row_bytes, 0),
-                             umma_idesc_f16(n * CoutG), 1u);
-                }
+                umma_f16(d0, make_desc(hi, a_kw + 2 * j), make_desc(hi, b_kw + rb0 + 2 * j), idesc_r0, 1u);
+                if (n1)
+                  umma_f16(d1, make_desc(hi, a_kw + 2 * j), make_desc(hi, b_kw + rb1 + 2 * j), idesc_r1, 1u);
               }
             }
-            umma_commit(sbase + SmemLayout::empty_a + 8 * s); // stage reusable once these MMAs retire
           }
-          // Output row r-1 has now received kh=0,1,2.
-          if (r - 1 >= it.y0 && r - 1 <= it.y1)
-          {
-            const uint32_t a_done = accbase + (uint32_t)(r - 1 - it.y0);
-            umma_commit(sbase + SmemLayout::tmem_full + 8 * ((R - 1) - (a_done % R)));
-          }
+          if (leader)
+            umma_commit(sbase + SmemLayout::empty_a + 8 * stage); // stage reusable once these MMAs retire
+          if (++stage == (uint32_t)NS) { stage = 0; sphase ^= 1; }
         }
-        accbase += (uint32_t)(it.y1 - it.y0 + 1);
+        // Output row r-1 has now received kh=0,1,2.
+        if (r - 1 >= it.y0 && r - 1 <= it.y1)
+        {
+          int m = (int)top_mod - 2;
+          if (m < 0) m += R;
+          if (leader)
+            umma_commit(sbase + SmemLayout::tmem_full + 8 * ((R - 1) - m));
+        }
+        if (++top_mod == (uint32_t)R) { top_mod = 0; top_par ^= 1; }
       }
+      const uint32_t tot = a_mod + (uint32_t)(it.y1 - it.y0 + 1);
+      a_par ^= (tot / R) & 1;
+      a_mod = tot % R;
     }
     __syncwarp();
   }
   // ---------------------------------------------------------------- epilogue
   else
   {
+    // 4 warps = 128 threads = the 128 TMEM lanes (pixels) of an accumulator. Per output row:
+    // TMEM -> registers -> +bias, ReLU, (pool) -> fp16 -> swizzled smem staging -> TMA store.
     const int q    = warp & 3;                  // TMEM lane quarter this warp may access
     const int lpix = q * 32 + lane;             // pixel within the strip
+    const bool issuer = (threadIdx.x == 64);    // first epilogue thread issues the TMA stores
     const float* bias_s = reinterpret_cast<const float*>(sgen + SmemLayout::bias);
     const int CoutG = p.CoutG;
-    const int cbase = group * CoutG;
-    __half* dst = reinterpret_cast<__half*>(p.dst);
     const bool pool = (p.post_op == POST_POOL);
     const int ystep = pool ? 2 : 1;
-    uint32_t accbase = 0;
+    const uint32_t out_region = b_region + p.b_bytes;
+    const int nbuf = p.out_nbuf;
+    const int spix = pool ? (lpix >> 1) : lpix; // staging row of this thread's pixel
+    const bool writer = !pool || ((lane & 1) == 0);
+    uint32_t a_mod = 0, a_par = 0;
+    uint32_t buf = 0;
     for (int item = cta; item < nitems; item += nctas)
     {
       const Item it = get_item(p, item);
-      const int x = it.x0 + lpix;
+      uint32_t y_mod = a_mod, y_par = a_par;
       for (int y = it.y0; y <= it.y1; y += ystep)
       {
-        const uint32_t a0 = accbase + (uint32_t)(y - it.y0);
-        const uint32_t slot0 = (R - 1) - (a0 % R);
-        const uint32_t slot1 = (R - 1) - ((a0 + 1) % R);
-        mbar_wait(sbase + SmemLayout::tmem_full + 8 * slot0, (a0 / R) & 1, 5);
+        const uint32_t slot0 = (R - 1) - y_mod;
+        const uint32_t par0 = y_par;
+        if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; }
+        const uint32_t slot1 = (R - 1) - y_mod;
+        const uint32_t par1 = y_par;
+        if (pool) { if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; } }
+
+        // staging buffer `buf` must have been read out by its previous TMA store
+        if (issuer)
+        {
+          if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
+        named_bar_sync(1, 128);
+
+        mbar_wait(sbase + SmemLayout::tmem_full + 8 * slot0, par0, 5);
         if (pool)
-          mbar_wait(sbase + SmemLayout::tmem_full + 8 * slot1, ((a0 + 1) / R) & 1, 6);
+          mbar_wait(sbase + SmemLayout::tmem_full + 8 * slot1, par1, 6);
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + slot0 * CoutG;
         const uint32_t t1 = tmem_base + ((uint32_t)(q * 32) << 16) + slot1 * CoutG;
-        for (int j = 0; j < CoutG; j += 16)
+        const uint32_t stage_out = out_region + buf * p.out_buf_bytes;
+        for (int oc = 0; oc < p.nout; ++oc)
         {
-          uint32_t v[16];
-          tmem_ld16(t0 + j, v);
-          float f[16];
-          if (pool)
+          const int c0 = p.out_c0[oc], ccw = p.out_cc[oc];
+          const uint32_t rowb = ccw * 2;
+          const uint32_t mask = (rowb >> 4) - 1;              // 16-B chunks per row - 1 (1,3,7)
+          const uint32_t piece = stage_out + p.out_off[oc];
+          for (int j = 0; j < ccw; j += 16)
           {
-            uint32_t w[16];
-            tmem_ld16(t1 + j, w);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-            {
-              float m = fmaxf(__uint_as_float(v[i]), __uint_as_float(w[i]));
-              m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-              f[i] = m;
-            }
-          }
-          else
-          {
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              f[i] = __uint_as_float(v[i]);
-          }
-          uint32_t h[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-          {
-            float a = f[2 * i] + bias_s[j + 2 * i];
-            float b = f[2 * i + 1] + bias_s[j + 2 * i + 1];
-            if (p.relu)
-            {
-              a = fmaxf(a, 0.f);
-              b = fmaxf(b, 0.f);
-            }
-            h[i] = pack_half2(a, b);
-          }
-          const int co = cbase + j;
-          if (x < p.W && co < p.CoutPad)
-          {
-            const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]);
-            const uint4 hi = make_uint4(h[4], h[5], h[6], h[7]);
+            uint32_t v[16];
+            float f[16];
+            tmem_ld16(t0 + c0 + j, v);
             if (pool)
             {
-              if ((lane & 1) == 0)
+              uint32_t w[16];
+              tmem_ld16(t1 + c0 + j, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
               {
-                const size_t o = ((size_t)(y >> 1) * (p.W >> 1) + (x >> 1)) * p.dstC + co;
-                *reinterpret_cast<uint4*>(dst + o)     = lo;
-                *reinterpret_cast<uint4*>(dst + o + 8) = hi;
+                float m = fmaxf(__uint_as_float(v[i]), __uint_as_float(w[i]));
+                f[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
               }
-            }
-            else if (p.post_op == POST_UPSAMPLE)
-            {
-#pragma unroll
-              for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx)
-                {
-                  const size_t o = ((size_t)(2 * y + dy) * (2 * p.W) + (2 * x + dx)) * p.dstC + co;
-                  *reinterpret_cast<uint4*>(dst + o)     = lo;
-                  *reinterpret_cast<uint4*>(dst + o + 8) = hi;
-                }
             }
             else
             {
-              const size_t o = ((size_t)y * p.W + x) * p.dstC + co;
-              *reinterpret_cast<uint4*>(dst + o)     = lo;
-              *reinterpret_cast<uint4*>(dst + o + 8) = hi;
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            }
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0 + j);
+            uint32_t h[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+              const float4 bb = b4[i];
+              float a0 = f[4 * i] + bb.x, a1 = f[4 * i + 1] + bb.y, a2 = f[4 * i + 2] + bb.z, a3 = f[4 * i + 3] + bb.w;
+              if (p.relu)
+              {
+                a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f);
+              }
+              h[2 * i] = pack_half2(a0, a1);
+              h[2 * i + 1] = pack_half2(a2, a3);
+            }
+            if (writer)
+            {
+              // swizzled staging row: 16-B chunk index XOR (128-B line index mod chunks-per-atom-row)
+              const uint32_t off0 = (uint32_t)spix * rowb + (uint32_t)j * 2;
+              const uint32_t sw0 = off0 ^ (((off0 >> 7) & mask) << 4);
+              const uint32_t off1 = off0 + 16;
+              const uint32_t sw1 = off1 ^ (((off1 >> 7) & mask) << 4);
+              st_shared_v4(piece + sw0, h[0], h[1], h[2], h[3]);
+              st_shared_v4(piece + sw1, h[4], h[5], h[6], h[7]);
             }
           }
         }
@@ -383,9 +400,24 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
           if (pool)
             mbar_arrive(sbase + SmemLayout::tmem_empty + 8 * slot1);
         }
+        // Make the generic-proxy smem writes visible to the TMA engine, then store the row.
+        fence_proxy_async();
+        named_bar_sync(2, 128);
+        if (issuer)
+        {
+          const int yo = pool ? (y >> 1) : y;
+          const int xo = pool ? (it.x0 >> 1) : it.x0;
+          for (int oc = 0; oc < p.nout; ++oc)
+            tma_store_3d(&p.omap[oc], stage_out + p.out_off[oc], group * CoutG + p.out_c0[oc], xo, yo);
+          bulk_commit();
+        }
+        if (++buf == (uint32_t)nbuf) buf = 0;
       }
-      accbase += (uint32_t)(it.y1 - it.y0 + 1);
+      const uint32_t tot = a_mod + (uint32_t)(it.y1 - it.y0 + 1);
+      a_par ^= (tot / R) & 1;
+      a_mod = tot % R;
     }
+    if (issuer) bulk_wait_read<0>();
   }
 
   // ---------------------------------------------------------------- teardown

@@ -102,6 +102,35 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
                : "memory");
 }
 
+// smem (shared::cta) -> global, clipped at the tensor bounds; completion tracked by bulk groups.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2)
+{
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+  asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------
@@ -172,6 +201,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t row_bytes
   d |= (uint64_t)(base_offset & 7u) << 49;                // base offset, bits [49,52)
   d |= (uint64_t)layout << 61;                            // swizzle mode, bits [61,64)
   return d;
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo)
+{
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
+
+// One lane of a converged warp.
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M=128, given N.
