@@ -87,7 +87,7 @@ OIDNB200_API int oidnb200_conv_launch_simt(const oidnb200_conv* conv, void* scra
 typedef struct oidnb200_conv_info
 {
   int grid, smem_bytes, ngroups, cout_group, nchunks, nstages, ring_slots, rows_per_item;
-  int nstrips, nrowchunks;
+  int nstrips, nrowchunks, nstreams;
 } oidnb200_conv_info;
 OIDNB200_API int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info);
 

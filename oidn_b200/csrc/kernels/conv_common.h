@@ -17,11 +17,12 @@ namespace oidnb200 {
 constexpr int kMaxChunks   = 8;     // K chunks (<=64 channels each) over both sources
 constexpr int kMaxOutChunks = 3;    // output-channel pieces (64/32/16) of one CoutG group
 constexpr int kMaxStages   = 8;     // A-operand pipeline depth
+constexpr int kConvThreads = 384;   // 2 x (TMA warp + MMA warp) + 2 x 4 epilogue warps
 constexpr int kStripW      = 128;   // output pixels per MMA tile (UMMA M)
 constexpr int kStageBytes  = 17408; // one A stage: up to 132 px x 128 B, 1024-aligned
 constexpr int kSmemHeader  = 2048;  // barriers + TMEM pointer + bias
 constexpr int kTmemCols    = 512;
-constexpr int kMaxSlots    = 32;
+constexpr int kMaxSlots    = 16;
 constexpr int kSmemBudget  = 232448; // 227 KB opt-in dynamic shared memory per CTA
 
 enum PostOp : int { POST_NONE = 0, POST_POOL = 1, POST_UPSAMPLE = 2 /* SIMT witness only */ };
@@ -40,9 +41,10 @@ struct ConvKernelParams
   uint32_t chunk_bblk[kMaxChunks];  // bytes of one kw block (3*CoutG rows)
   int      H, W;                    // conv resolution (= resolution of the unpooled output)
   int      CoutG, ngroups, CoutPad; // output channels per CTA group / groups / padded total
-  int      R;                       // TMEM accumulator ring slots (R*CoutG <= 512)
+  int      nstreams;                // 1 or 2 independent row streams per CTA
+  int      R;                       // TMEM accumulator ring slots per stream (nstreams*R*CoutG <= 512)
   int      RC, nstrips, nrowchunks; // rows per work item, strips across W, row chunks down H
-  int      nstages;                 // A pipeline stages
+  int      nstages;                 // A pipeline stages per stream
   uint32_t w_bytes;                 // total weight bytes TMA-loaded per CTA
   uint32_t b_bytes;                 // size of the resident weight region (1024-aligned blocks)
   int      nout;                    // output pieces of the group
@@ -50,7 +52,7 @@ struct ConvKernelParams
   int      out_cc[kMaxOutChunks];   // channels in the piece (64/32/16)
   uint32_t out_off[kMaxOutChunks];  // byte offset of the piece inside one staging buffer
   uint32_t out_buf_bytes;           // bytes of one staging buffer
-  int      out_nbuf;                // 1 or 2 staging buffers
+  int      out_nbuf;                // 1 or 2 staging buffers per epilogue warpgroup (two warpgroups)
   int      relu, post_op;
   const float* bias;                // fp32 [CoutAlloc]
 };

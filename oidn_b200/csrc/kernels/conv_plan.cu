@@ -180,8 +180,8 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
     return align_up(off, 1024);
   };
   int CoutG = std::min(d.Cout, 128);
-  while (CoutG > 16 && b_bytes(CoutG) + out_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
-  if (b_bytes(CoutG) + out_bytes(CoutG) + min_stages * stage_bytes > avail)
+  while (CoutG > 16 && b_bytes(CoutG) + 2 * out_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
+  if (b_bytes(CoutG) + 2 * out_bytes(CoutG) + min_stages * stage_bytes > avail)
   {
     set_error("conv: weights for 16 output channels do not fit in shared memory");
     return OIDNB200_ERR_UNSUPPORTED;
@@ -192,7 +192,6 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   kp.ngroups = ngroups;
   kp.CoutPad = d.Cout;
   pl.CoutAlloc = CoutG * ngroups;
-  kp.R = std::min(kMaxSlots, kTmemCols / CoutG);
 
   uint32_t off = 0;
   for (int c = 0; c < n; ++c)
@@ -221,19 +220,22 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   }
   kp.out_buf_bytes = align_up(ooff, 1024);
 
-  // split what is left between a second staging buffer and A stages (>= 3 stages before double
-  // buffering the output)
-  uint32_t left = avail - bbytes - kp.out_buf_bytes;
-  kp.out_nbuf = (left >= kp.out_buf_bytes + 3 * stage_bytes) ? 2 : 1;
-  if (kp.out_nbuf == 2) left -= kp.out_buf_bytes;
-  int nstages = std::min((int)(left / stage_bytes), kMaxStages);
-  kp.nstages = nstages;
-  pl.smem = 1024 + kSmemHeader + (size_t)nstages * stage_bytes + bbytes + (size_t)kp.out_nbuf * kp.out_buf_bytes;
+  // What is left after weights and one staging buffer per epilogue warpgroup goes to A stages.
+  // Two streams need a 4-slot accumulator ring each (CoutG <= 64) and >= 2 stages each.
+  uint32_t left = avail - bbytes - 2 * kp.out_buf_bytes;
+  kp.out_nbuf = 1;
+  int total_stages = (int)(left / stage_bytes);
+  kp.nstreams = (CoutG <= 64 && total_stages >= 4) ? 2 : 1;
+  kp.nstages = std::min(total_stages / kp.nstreams, kMaxStages);
+  kp.R = std::min(kMaxSlots, (kTmemCols / kp.nstreams) / CoutG);
+  pl.smem = 1024 + kSmemHeader + (size_t)kp.nstreams * kp.nstages * stage_bytes + bbytes +
+            (size_t)2 * kp.out_nbuf * kp.out_buf_bytes;
 
   // Work decomposition: strips of 128 px x RC rows; pick RC minimising the critical path.
   kp.H = d.H; kp.W = d.W;
   kp.nstrips = (d.W + kStripW - 1) / kStripW;
-  const int P = std::max(1, num_sms() / ngroups);
+  const int Pc = std::max(1, num_sms() / ngroups);      // physical CTAs per output-channel group
+  const int P = Pc * kp.nstreams;                        // independent row streams per group
   const int step = (d.post_op == POST_POOL) ? 2 : 1;
   int bestRC = step;
   long bestCost = -1;
@@ -251,7 +253,7 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   kp.RC = bestRC;
   kp.nrowchunks = (d.H + bestRC - 1) / bestRC;
   const int items = kp.nstrips * kp.nrowchunks;
-  pl.grid = std::min(P, items) * ngroups;
+  pl.grid = std::min(Pc, (items + kp.nstreams - 1) / kp.nstreams) * ngroups;
 
   kp.relu = d.relu;
   kp.post_op = d.post_op;
@@ -536,6 +538,7 @@ int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info)
   info->rows_per_item = pl.kp.RC;
   info->nstrips = pl.kp.nstrips;
   info->nrowchunks = pl.kp.nrowchunks;
+  info->nstreams = pl.kp.nstreams;
   return 0;
 }
 

@@ -26,9 +26,9 @@ int main(int argc, char** argv)
   oidnb200_conv* conv = nullptr;
   if (oidnb200_conv_create(&d, &conv)) { printf("create failed: %s\n", oidnb200_last_error()); return 3; }
   oidnb200_conv_info info; oidnb200_conv_get_info(conv, &info);
-  printf("cfg H=%d W=%d C1=%d C2=%d Cout=%d post=%d up=%d mode=%d | grid=%d smem=%d groups=%d CoutG=%d chunks=%d stages=%d R=%d RC=%d\n",
+  printf("cfg H=%d W=%d C1=%d C2=%d Cout=%d post=%d up=%d mode=%d | grid=%d smem=%d groups=%d CoutG=%d chunks=%d stages=%d R=%d RC=%d streams=%d\n",
          d.H, d.W, d.C1, d.C2, d.Cout, d.post_op, d.src1_upsampled, d.shift_mode, info.grid, info.smem_bytes,
-         info.ngroups, info.cout_group, info.nchunks, info.nstages, info.ring_slots, info.rows_per_item);
+         info.ngroups, info.cout_group, info.nchunks, info.nstages, info.ring_slots, info.rows_per_item, info.nstreams);
 
   const int H1 = d.src1_upsampled ? d.H / 2 : d.H, W1 = d.src1_upsampled ? d.W / 2 : d.W;
   const size_t n1 = (size_t)H1 * W1 * d.C1, n2 = (size_t)d.H * d.W * d.C2;
