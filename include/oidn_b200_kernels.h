@@ -91,6 +91,80 @@ typedef struct oidnb200_conv_info
 } oidnb200_conv_info;
 OIDNB200_API int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info);
 
+/* ------------------------------------------------------------------------------------------
+ * Images, tiles, transfer functions  -- core/image.h:14-120, core/tile.h, core/color.h:10-166
+ * ------------------------------------------------------------------------------------------ */
+/* Pixel formats use the public API's numbering (include/OpenImageDenoise/oidn.h:239-254). */
+enum
+{
+  OIDNB200_FORMAT_UNDEFINED = 0,
+  OIDNB200_FORMAT_FLOAT = 1, OIDNB200_FORMAT_FLOAT2 = 2, OIDNB200_FORMAT_FLOAT3 = 3,
+  OIDNB200_FORMAT_HALF = 257, OIDNB200_FORMAT_HALF2 = 258, OIDNB200_FORMAT_HALF3 = 259
+};
+
+/* A strided 1-3 channel image exactly as given to oidnSetSharedFilterImage: device, managed or
+ * pinned-host memory (anything the GPU can dereference). ptr == NULL means "image not set". */
+typedef struct oidnb200_image
+{
+  void* ptr;
+  int format;          /* OIDNB200_FORMAT_* */
+  int W, H;
+  size_t pixel_stride; /* bytes */
+  size_t row_stride;   /* bytes */
+} oidnb200_image;
+
+/* core/tile.h: source/destination origin and size of the rectangle an op works on. */
+typedef struct oidnb200_tile
+{
+  int hSrcBegin, wSrcBegin, hDstBegin, wDstBegin, H, W;
+} oidnb200_tile;
+
+enum { OIDNB200_TF_LINEAR = 0, OIDNB200_TF_SRGB = 1, OIDNB200_TF_PU = 2, OIDNB200_TF_LOG = 3 };
+
+/* TransferFunction (core/color.h:10-166): type + input scale, either a value or a device pointer
+ * to the autoexposure result (core/color.h:110-123). The PU/Log normalisation 1/forward(65504)
+ * (core/color.cpp:9-16) is derived inside. */
+typedef struct oidnb200_transfer
+{
+  int type;                     /* OIDNB200_TF_* */
+  float input_scale;            /* used when input_scale_ptr == NULL */
+  const float* input_scale_ptr; /* device pointer or NULL */
+} oidnb200_transfer;
+
+/* InputProcess::submitKernels (core/input_process.h, devices/gpu/gpu_input_process.h:82-176):
+ * fills the whole [TH][TW][C] fp16 tile buffer (C = 16: 3/6/9 used channels, rest zero; zero
+ * outside the tile footprint). `color` is the main input (color, or albedo/normal when filtering
+ * an auxiliary image alone); albedo/normal may have ptr == NULL. */
+OIDNB200_API int oidnb200_input_process_launch(const oidnb200_image* color, const oidnb200_image* albedo,
+                                               const oidnb200_image* normal, const oidnb200_tile* tile,
+                                               const oidnb200_transfer* tf, int hdr, int snorm,
+                                               void* dst, int TH, int TW, int C, oidnb200_stream stream);
+
+/* OutputProcess::submitKernels (core/output_process.h, devices/gpu/gpu_output_process.h:35-73):
+ * reads channels 0..2 of the [TH][TW][C] fp16 tensor at tile.{h,w}SrcBegin and writes the
+ * tile.H x tile.W rectangle at tile.{h,w}DstBegin of the output image. */
+OIDNB200_API int oidnb200_output_process_launch(const void* src, int TH, int TW, int C,
+                                                const oidnb200_tile* tile, const oidnb200_transfer* tf,
+                                                int hdr, int snorm, const oidnb200_image* dst,
+                                                oidnb200_stream stream);
+
+/* Autoexposure (core/autoexposure.h:14-53, devices/gpu/gpu_autoexposure.h:13-164): one launch,
+ * result = 0.18 / exp2(mean log2 of the bin luminances > 1e-8) (1 if none) stored to *dst
+ * (device float). scratch: device memory of oidnb200_autoexposure_scratch_bytes(H, W). */
+OIDNB200_API size_t oidnb200_autoexposure_scratch_bytes(int H, int W);
+OIDNB200_API int oidnb200_autoexposure_launch(const oidnb200_image* src, void* scratch, float* dst,
+                                              oidnb200_stream stream);
+
+/* ImageCopy (core/image_copy.h, devices/gpu/gpu_image_copy.h:15-27): same format and size. */
+OIDNB200_API int oidnb200_image_copy_launch(const oidnb200_image* src, const oidnb200_image* dst,
+                                            oidnb200_stream stream);
+
+/* Stand-alone Pool / Upsample (core/pool.h, core/upsample.h; devices/gpu/gpu_pool.h:33-52,
+ * gpu_upsample.h:33-52) on [H][W][C] fp16 tensors, C a multiple of 8. The UNet graph never
+ * launches these (both are fused into the convolutions); they complete the Engine op surface. */
+OIDNB200_API int oidnb200_pool_launch(const void* src, int H, int W, int C, void* dst, oidnb200_stream stream);
+OIDNB200_API int oidnb200_upsample_launch(const void* src, int H, int W, int C, void* dst, oidnb200_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

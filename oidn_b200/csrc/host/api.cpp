@@ -1,0 +1,402 @@
+// C entry points of include/oidn_b200.h. Same structure as the reference's api/api.cpp:
+// handle cast, per-device mutex around every call (api/api.cpp:42-69), exceptions converted to
+// the device's first-error slot (api/api.cpp:17-31).
+#include "../../../include/oidn_b200.h"
+#include "filter.hpp"
+#include <atomic>
+#include <cuda_runtime.h>
+#include <cstring>
+
+using namespace oidnb200;
+
+struct oidnb200_device_t
+{
+  std::atomic<int> refs{1};
+  std::unique_ptr<Device> impl;
+};
+
+struct oidnb200_buffer_t
+{
+  std::atomic<int> refs{1};
+  oidnb200_device_t* device;
+  void* ptr = nullptr;
+  size_t size = 0;
+  Storage storage = Storage::Device;
+};
+
+struct oidnb200_filter_t
+{
+  std::atomic<int> refs{1};
+  oidnb200_device_t* device;
+  std::shared_ptr<Filter> impl;
+};
+
+namespace {
+
+void reportError(oidnb200_device_t* d, Error code, const std::string& msg)
+{
+  if (d && d->impl) d->impl->setError(code, msg); else Device::setGlobalError(code, msg);
+}
+
+template <typename F>
+void guarded(oidnb200_device_t* d, F&& f)
+{
+  try
+  {
+    if (!d || !d->impl) throw Exception(Error::InvalidArgument, "invalid handle");
+    std::lock_guard<std::mutex> lock(d->impl->getMutex());
+    f();
+  }
+  catch (const Exception& e) { reportError(d, e.code(), e.what()); }
+  catch (const std::bad_alloc&) { reportError(d, Error::OutOfMemory, "out of memory"); }
+  catch (const std::exception& e) { reportError(d, Error::Unknown, e.what()); }
+  catch (...) { reportError(d, Error::Unknown, "unknown exception caught"); }
+}
+
+void retainDevice(oidnb200_device_t* d) { d->refs.fetch_add(1); }
+void releaseDevice(oidnb200_device_t* d)
+{
+  if (d->refs.fetch_sub(1) == 1)
+  {
+    try { if (d->impl && d->impl->isCommitted()) d->impl->wait(); } catch (...) {}
+    delete d;
+  }
+}
+
+void checkString(const char* s)
+{
+  if (!s) throw Exception(Error::InvalidArgument, "string pointer is null");
+}
+
+Image makeImage(void* base, int format, size_t width, size_t height, size_t byteOffset, size_t pixelStride,
+                size_t rowStride)
+{
+  // core/image.cpp:41-48 + ImageDesc checks (core/image.cpp:11-39)
+  Image im;
+  const Format f = static_cast<Format>(format);
+  if (formatChannels(f) == 0 && base) throw Exception(Error::InvalidArgument, "invalid image format");
+  if (width > 65536 || height > 65536) throw Exception(Error::InvalidArgument, "image size too large");
+  const size_t px = formatBytes(f);
+  if (pixelStride == 0) pixelStride = px;
+  else if (pixelStride < px) throw Exception(Error::InvalidArgument, "pixel stride smaller than pixel size");
+  if (rowStride == 0) rowStride = width * pixelStride;
+  else if (rowStride < width * pixelStride) throw Exception(Error::InvalidArgument, "row stride smaller than width * pixel stride");
+  if (base && (pixelStride % (formatIsHalf(f) ? 2 : 4) || rowStride % (formatIsHalf(f) ? 2 : 4) ||
+               (reinterpret_cast<uintptr_t>(base) + byteOffset) % (formatIsHalf(f) ? 2 : 4)))
+    throw Exception(Error::InvalidArgument, "image pointer and strides must be aligned to the channel type");
+  im.ptr = base ? static_cast<uint8_t*>(base) + byteOffset : nullptr;
+  im.format = f;
+  im.W = (int)width; im.H = (int)height;
+  im.pixelStride = pixelStride; im.rowStride = rowStride;
+  return im;
+}
+
+} // namespace
+
+extern "C" {
+
+int oidnb200GetNumPhysicalDevices(void) { return oidnb200_device_count(); }
+
+OIDNB200Device oidnb200NewCUDADevice(const int* deviceIDs, void* const* streams, int numPairs)
+{
+  try
+  {
+    if (!deviceIDs || numPairs < 1) throw Exception(Error::InvalidArgument, "invalid number of CUDA device/stream pairs");
+    std::vector<int> ids(deviceIDs, deviceIDs + numPairs);
+    std::vector<void*> st(numPairs, nullptr);
+    if (streams) for (int i = 0; i < numPairs; ++i) st[i] = streams[i];
+    auto* d = new oidnb200_device_t();
+    d->impl.reset(new Device(ids, st));
+    return d;
+  }
+  catch (const Exception& e) { Device::setGlobalError(e.code(), e.what()); }
+  catch (const std::exception& e) { Device::setGlobalError(Error::Unknown, e.what()); }
+  return nullptr;
+}
+
+OIDNB200Device oidnb200NewDevice(void)
+{
+  const int id = 0;
+  return oidnb200NewCUDADevice(&id, nullptr, 1);
+}
+
+void oidnb200RetainDevice(OIDNB200Device d) { if (d) retainDevice(d); }
+void oidnb200ReleaseDevice(OIDNB200Device d) { if (d) releaseDevice(d); }
+
+void oidnb200SetDeviceInt(OIDNB200Device d, const char* name, int value)
+{
+  guarded(d, [&] { checkString(name); d->impl->setInt(name, value); });
+}
+
+int oidnb200GetDeviceInt(OIDNB200Device d, const char* name)
+{
+  int v = 0;
+  guarded(d, [&] { checkString(name); v = d->impl->getInt(name); });
+  return v;
+}
+
+void oidnb200SetDeviceString(OIDNB200Device d, const char* name, const char* value)
+{
+  guarded(d, [&] { checkString(name); checkString(value); d->impl->setString(name, value); });
+}
+
+void oidnb200CommitDevice(OIDNB200Device d) { guarded(d, [&] { d->impl->commit(); }); }
+void oidnb200SyncDevice(OIDNB200Device d) { guarded(d, [&] { d->impl->checkCommitted(); d->impl->wait(); }); }
+
+int oidnb200GetDeviceError(OIDNB200Device d, const char** outMessage)
+{
+  if (!d || !d->impl) return (int)Device::getGlobalError(outMessage);
+  std::lock_guard<std::mutex> lock(d->impl->getMutex());
+  return (int)d->impl->getError(outMessage);
+}
+
+// ---- buffers ----------------------------------------------------------------------------------
+OIDNB200Buffer oidnb200NewBufferWithStorage(OIDNB200Device d, size_t byteSize, int storage)
+{
+  oidnb200_buffer_t* b = nullptr;
+  guarded(d, [&] {
+    d->impl->checkCommitted();
+    const Storage s = static_cast<Storage>(storage);
+    if (s != Storage::Host && s != Storage::Device && s != Storage::Managed)
+      throw Exception(Error::InvalidArgument, "invalid storage mode");
+    void* p = d->impl->getEngine(0)->malloc(byteSize, s);
+    b = new oidnb200_buffer_t();
+    b->device = d; b->ptr = p; b->size = byteSize; b->storage = s;
+    retainDevice(d);
+  });
+  return b;
+}
+
+OIDNB200Buffer oidnb200NewBuffer(OIDNB200Device d, size_t byteSize)
+{
+  return oidnb200NewBufferWithStorage(d, byteSize, (int)Storage::Device);
+}
+
+void* oidnb200GetBufferData(OIDNB200Buffer b) { return b ? b->ptr : nullptr; }
+size_t oidnb200GetBufferSize(OIDNB200Buffer b) { return b ? b->size : 0; }
+
+static void bufferCopy(oidnb200_buffer_t* b, size_t off, size_t n, void* dst, const void* src, bool read, bool sync)
+{
+  if (!b) return;
+  guarded(b->device, [&] {
+    if (off + n > b->size || off + n < off) throw Exception(Error::InvalidArgument, "buffer region is out of bounds");
+    if (n == 0) return;
+    if ((read && !dst) || (!read && !src)) throw Exception(Error::InvalidArgument, "host pointer is null");
+    Engine* e = b->device->impl->getEngine(0);
+    uint8_t* p = static_cast<uint8_t*>(b->ptr) + off;
+    if (read) e->submitCopy(dst, p, n); else e->submitCopy(p, src, n);
+    if (sync) e->wait();
+  });
+}
+
+void oidnb200ReadBuffer(OIDNB200Buffer b, size_t off, size_t n, void* dst) { bufferCopy(b, off, n, dst, nullptr, true, true); }
+void oidnb200WriteBuffer(OIDNB200Buffer b, size_t off, size_t n, const void* src) { bufferCopy(b, off, n, nullptr, src, false, true); }
+void oidnb200ReadBufferAsync(OIDNB200Buffer b, size_t off, size_t n, void* dst) { bufferCopy(b, off, n, dst, nullptr, true, false); }
+void oidnb200WriteBufferAsync(OIDNB200Buffer b, size_t off, size_t n, const void* src) { bufferCopy(b, off, n, nullptr, src, false, false); }
+
+void oidnb200ReleaseBuffer(OIDNB200Buffer b)
+{
+  if (!b) return;
+  if (b->refs.fetch_sub(1) == 1)
+  {
+    oidnb200_device_t* d = b->device;
+    guarded(d, [&] { d->impl->wait(); d->impl->getEngine(0)->free(b->ptr, b->storage); });
+    delete b;
+    releaseDevice(d);
+  }
+}
+
+// ---- filters ----------------------------------------------------------------------------------
+OIDNB200Filter oidnb200NewFilter(OIDNB200Device d, const char* type)
+{
+  oidnb200_filter_t* f = nullptr;
+  guarded(d, [&] {
+    checkString(type);
+    auto impl = d->impl->newFilter(type);
+    f = new oidnb200_filter_t();
+    f->device = d; f->impl = impl;
+    retainDevice(d);
+  });
+  return f;
+}
+
+void oidnb200RetainFilter(OIDNB200Filter f) { if (f) f->refs.fetch_add(1); }
+
+void oidnb200ReleaseFilter(OIDNB200Filter f)
+{
+  if (!f) return;
+  if (f->refs.fetch_sub(1) == 1)
+  {
+    oidnb200_device_t* d = f->device;
+    guarded(d, [&] { d->impl->wait(); f->impl.reset(); }); // api/api.cpp:111-141: wait for idle, then destroy
+    delete f;
+    releaseDevice(d);
+  }
+}
+
+void oidnb200SetFilterImage(OIDNB200Filter f, const char* name, OIDNB200Buffer buffer, int format, size_t width,
+                            size_t height, size_t byteOffset, size_t pixelByteStride, size_t rowByteStride)
+{
+  if (!f) return;
+  guarded(f->device, [&] {
+    checkString(name);
+    if (!buffer) throw Exception(Error::InvalidArgument, "buffer is null");
+    Image im = makeImage(buffer->ptr, format, width, height, byteOffset, pixelByteStride, rowByteStride);
+    if (im && im.end() > static_cast<uint8_t*>(buffer->ptr) + buffer->size)
+      throw Exception(Error::InvalidArgument, "buffer region is out of bounds");
+    f->impl->setImage(name, im);
+  });
+}
+
+void oidnb200SetSharedFilterImage(OIDNB200Filter f, const char* name, void* devPtr, int format, size_t width,
+                                  size_t height, size_t byteOffset, size_t pixelByteStride, size_t rowByteStride)
+{
+  if (!f) return;
+  guarded(f->device, [&] {
+    checkString(name);
+    f->impl->setImage(name, makeImage(devPtr, format, width, height, byteOffset, pixelByteStride, rowByteStride));
+  });
+}
+
+void oidnb200UnsetFilterImage(OIDNB200Filter f, const char* name)
+{
+  if (f) guarded(f->device, [&] { checkString(name); f->impl->unsetImage(name); });
+}
+
+void oidnb200SetSharedFilterData(OIDNB200Filter f, const char* name, void* hostPtr, size_t byteSize)
+{
+  if (!f) return;
+  guarded(f->device, [&] {
+    checkString(name);
+    if (!hostPtr && byteSize) throw Exception(Error::InvalidArgument, "data pointer is null but the size is not zero");
+    Data d;
+    d.ptr = byteSize ? hostPtr : nullptr; d.size = byteSize;
+    f->impl->setData(name, d);
+  });
+}
+
+void oidnb200UpdateFilterData(OIDNB200Filter f, const char* name)
+{
+  if (f) guarded(f->device, [&] { checkString(name); f->impl->updateData(name); });
+}
+
+void oidnb200UnsetFilterData(OIDNB200Filter f, const char* name)
+{
+  if (f) guarded(f->device, [&] { checkString(name); f->impl->unsetData(name); });
+}
+
+void oidnb200SetFilterBool(OIDNB200Filter f, const char* name, bool value)
+{
+  if (f) guarded(f->device, [&] { checkString(name); f->impl->setInt(name, value ? 1 : 0); });
+}
+
+bool oidnb200GetFilterBool(OIDNB200Filter f, const char* name)
+{
+  int v = 0;
+  if (f) guarded(f->device, [&] { checkString(name); v = f->impl->getInt(name); });
+  return v != 0;
+}
+
+void oidnb200SetFilterInt(OIDNB200Filter f, const char* name, int value)
+{
+  if (f) guarded(f->device, [&] { checkString(name); f->impl->setInt(name, value); });
+}
+
+int oidnb200GetFilterInt(OIDNB200Filter f, const char* name)
+{
+  int v = 0;
+  if (f) guarded(f->device, [&] { checkString(name); v = f->impl->getInt(name); });
+  return v;
+}
+
+void oidnb200SetFilterFloat(OIDNB200Filter f, const char* name, float value)
+{
+  if (f) guarded(f->device, [&] { checkString(name); f->impl->setFloat(name, value); });
+}
+
+float oidnb200GetFilterFloat(OIDNB200Filter f, const char* name)
+{
+  float v = 0.f;
+  if (f) guarded(f->device, [&] { checkString(name); v = f->impl->getFloat(name); });
+  return v;
+}
+
+void oidnb200SetFilterProgressMonitorFunction(OIDNB200Filter f, OIDNB200ProgressMonitorFunction func, void* userPtr)
+{
+  if (f) guarded(f->device, [&] { f->impl->setProgressMonitorFunction(func, userPtr); });
+}
+
+void oidnb200CommitFilter(OIDNB200Filter f) { if (f) guarded(f->device, [&] { f->impl->commit(); }); }
+void oidnb200ExecuteFilter(OIDNB200Filter f) { if (f) guarded(f->device, [&] { f->impl->execute(SyncMode::Blocking); }); }
+void oidnb200ExecuteFilterAsync(OIDNB200Filter f) { if (f) guarded(f->device, [&] { f->impl->execute(SyncMode::Async); }); }
+
+void oidnb200GetFilterInfo(OIDNB200Filter f, oidnb200_filter_info* info)
+{
+  if (!f || !info) return;
+  memset(info, 0, sizeof(*info));
+  guarded(f->device, [&] {
+    auto* u = dynamic_cast<UNetFilter*>(f->impl.get());
+    if (!u) return;
+    const TilePlan& p = u->getTilePlan();
+    info->tileH = p.tileH; info->tileW = p.tileW; info->tileCountH = p.tileCountH; info->tileCountW = p.tileCountW;
+    info->tileOverlap = p.tileOverlap; info->tileAlignment = p.tileAlignment;
+    info->largeModel = u->isLargeModel();
+    info->memoryBytes = u->getScratchByteSize();
+  });
+}
+
+void oidnb200PlanTiles(int H, int W, int largeModel, int deviceMinAlignment, int numEngines, long maxTilePixels,
+                       oidnb200_tile_plan* out)
+{
+  const TilePlan p = planTiles(H, W, largeModel != 0, deviceMinAlignment, numEngines > 0 ? numEngines : 1,
+                               maxTilePixels > 0 ? maxTilePixels : 2160L * 2160L, [](const TilePlan&) { return true; });
+  *out = oidnb200_tile_plan{p.H, p.W, p.tileH, p.tileW, p.tilePadH, p.tilePadW, p.tileCountH, p.tileCountW,
+                            p.tileAlignment, p.tileOverlap};
+}
+
+int oidnb200EnumerateTiles(const oidnb200_tile_plan* pl, int* out, int maxTiles)
+{
+  TilePlan p;
+  p.H = pl->H; p.W = pl->W; p.tileH = pl->tileH; p.tileW = pl->tileW; p.tilePadH = pl->tilePadH; p.tilePadW = pl->tilePadW;
+  p.tileCountH = pl->tileCountH; p.tileCountW = pl->tileCountW; p.tileAlignment = pl->tileAlignment; p.tileOverlap = pl->tileOverlap;
+  const std::vector<TileRect> t = enumerateTiles(p);
+  for (int i = 0; i < (int)t.size() && i < maxTiles; ++i)
+  {
+    const int v[12] = {t[i].hSrc, t[i].wSrc, t[i].hBuf, t[i].wBuf, t[i].H1, t[i].W1,
+                       t[i].hOutBuf, t[i].wOutBuf, t[i].hDst, t[i].wDst, t[i].H2, t[i].W2};
+    memcpy(out + 12 * i, v, sizeof(v));
+  }
+  return (int)t.size();
+}
+
+int oidnb200ParseTZA(const void* blob, size_t size, const char** outMessage)
+{
+  static thread_local std::string msg;
+  try
+  {
+    auto m = parseTZA(blob, size);
+    if (outMessage) *outMessage = nullptr;
+    return (int)m->size();
+  }
+  catch (const Exception& e)
+  {
+    msg = e.what();
+    if (outMessage) *outMessage = msg.c_str();
+    return -(int)e.code();
+  }
+}
+
+size_t oidnb200PlanArena(int n, const size_t* sizes, const int* firstOp, const int* lastOp, size_t* offsets)
+{
+  ArenaPlanner pl;
+  for (int i = 0; i < n; ++i)
+  {
+    const int id = pl.newAlloc(firstOp[i], sizes[i]);
+    pl.addDep(lastOp[i], id);
+  }
+  pl.commit();
+  for (int i = 0; i < n; ++i) offsets[i] = pl.getAllocByteOffset(i);
+  return pl.validate() ? pl.getByteSize() : (size_t)-1;
+}
+
+} // extern "C"

@@ -1,0 +1,200 @@
+#include "device.hpp"
+#include "filter.hpp"
+#include <cuda_runtime.h>
+#include <cstdlib>
+
+namespace oidnb200 {
+
+namespace {
+std::mutex g_globalMutex;
+Error g_globalCode = Error::None;
+std::string g_globalMessage;
+thread_local std::string g_globalMessageOut;
+} // namespace
+
+Device::Device(const std::vector<int>& ids, const std::vector<void*>& streams)
+  : deviceIDs(ids), userStreams(streams)
+{
+  if (ids.empty() || ids.size() > 16) throw Exception(Error::InvalidArgument, "invalid number of CUDA device/stream pairs");
+  userStreams.resize(ids.size(), nullptr);
+  for (size_t i = 0; i < ids.size(); ++i)
+    for (size_t j = i + 1; j < ids.size(); ++j)
+      if (ids[i] == ids[j]) throw Exception(Error::InvalidArgument, "duplicate CUDA device ID");
+  // 4K (3840x2176 tile buffer) is one tile on a B200; the reference's default of 2160x2160
+  // (core/unet_filter.h:39) exists for GPUs with little memory.
+  maxTilePixels = 3840L * 2176L;
+  if (const char* e = getenv("OIDN_B200_MAX_TILE_PIXELS")) maxTilePixels = atol(e);
+  if (const char* e = getenv("OIDN_B200_WEIGHTS_DIR")) weightsDir = e;
+  if (const char* e = getenv("OIDN_VERBOSE")) verbose = atoi(e);
+}
+
+Device::~Device()
+{
+  for (size_t i = 0; i < events.size(); ++i)
+  {
+    cudaSetDevice(deviceIDs[i]);
+    if (events[i]) cudaEventDestroy(static_cast<cudaEvent_t>(events[i]));
+  }
+}
+
+void Device::checkCommitted() const
+{
+  if (!committed) throw Exception(Error::InvalidOperation, "changes to the device are not committed");
+}
+
+void Device::commit()
+{
+  if (committed) throw Exception(Error::InvalidOperation, "device can be committed only once");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+  {
+    cudaGetLastError();
+    throw Exception(Error::UnsupportedHardware, "no CUDA device found");
+  }
+  for (int id : deviceIDs)
+  {
+    if (id < 0 || id >= count) throw Exception(Error::InvalidArgument, "invalid CUDA device ID");
+    int major = 0;
+    checkCuda(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, id), "cudaDeviceGetAttribute");
+    if (major != 10)
+      throw Exception(Error::UnsupportedHardware, "the B200 backend needs a compute capability 10.x GPU (sm_100a kernels)");
+  }
+  for (size_t i = 0; i < deviceIDs.size(); ++i)
+  {
+    engines.emplace_back(new Engine(deviceIDs[i], userStreams[i]));
+    cudaEvent_t ev;
+    checkCuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+    events.push_back(ev);
+  }
+  // all-pairs peer access: any engine may read the input images / write the output image in place
+  for (size_t i = 0; i < deviceIDs.size(); ++i)
+    for (size_t j = 0; j < deviceIDs.size(); ++j)
+    {
+      if (i == j) continue;
+      int can = 0;
+      checkCuda(cudaDeviceCanAccessPeer(&can, deviceIDs[i], deviceIDs[j]), "cudaDeviceCanAccessPeer");
+      if (!can) throw Exception(Error::UnsupportedHardware, "CUDA devices of a multi-GPU device must be peer accessible");
+      checkCuda(cudaSetDevice(deviceIDs[i]), "cudaSetDevice");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(deviceIDs[j], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) checkCuda(e, "cudaDeviceEnablePeerAccess");
+      cudaGetLastError();
+    }
+  committed = true;
+}
+
+void Device::submitBarrier()
+{
+  if (engines.size() == 1) return; // a single stream is already ordered
+  cudaStream_t s0 = static_cast<cudaStream_t>(engines[0]->getStream());
+  for (size_t i = 1; i < engines.size(); ++i)
+  {
+    engines[i]->makeCurrent();
+    checkCuda(cudaEventRecord(static_cast<cudaEvent_t>(events[i]), static_cast<cudaStream_t>(engines[i]->getStream())), "cudaEventRecord");
+    checkCuda(cudaStreamWaitEvent(s0, static_cast<cudaEvent_t>(events[i]), 0), "cudaStreamWaitEvent");
+  }
+  engines[0]->makeCurrent();
+  checkCuda(cudaEventRecord(static_cast<cudaEvent_t>(events[0]), s0), "cudaEventRecord");
+  for (size_t i = 1; i < engines.size(); ++i)
+    checkCuda(cudaStreamWaitEvent(static_cast<cudaStream_t>(engines[i]->getStream()), static_cast<cudaEvent_t>(events[0]), 0), "cudaStreamWaitEvent");
+}
+
+void Device::wait()
+{
+  for (auto& e : engines) e->wait();
+}
+
+std::shared_ptr<Filter> Device::newFilter(const std::string& type)
+{
+  checkCommitted();
+  if (type == "RT") return std::make_shared<RTFilter>(this);
+  if (type == "RTLightmap") return std::make_shared<RTLightmapFilter>(this);
+  throw Exception(Error::InvalidArgument, "unknown filter type: '" + type + "'"); // core/device.cpp:283-298
+}
+
+void Device::setInt(const std::string& name, int value)
+{
+  if (name == "verbose") verbose = value;
+  else if (name == "maxTilePixels") maxTilePixels = value; // backend specific
+  else if (committed) throw Exception(Error::InvalidOperation, "device can be committed only once");
+  else throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
+}
+
+int Device::getInt(const std::string& name) const
+{
+  if (name == "type") return 3; // OIDN_DEVICE_TYPE_CUDA
+  if (name == "version") return 20401;
+  if (name == "versionMajor") return 2;
+  if (name == "versionMinor") return 4;
+  if (name == "versionPatch") return 1;
+  if (name == "verbose") return verbose;
+  if (name == "numSubdevices") return (int)deviceIDs.size();
+  if (name == "maxTilePixels") return (int)maxTilePixels;
+  if (name == "systemMemorySupported" || name == "managedMemorySupported")
+  {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, name[0] == 's' ? cudaDevAttrPageableMemoryAccess : cudaDevAttrManagedMemory, deviceIDs[0]);
+    cudaGetLastError();
+    return v;
+  }
+  throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
+}
+
+void Device::setString(const std::string& name, const std::string& value)
+{
+  if (name == "weightsDir") weightsDir = value;
+  else throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
+}
+
+Storage Device::getPtrStorage(const void* ptr) const
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return Storage::Undefined;
+  }
+  switch (a.type)
+  {
+  case cudaMemoryTypeHost:    return Storage::Host;
+  case cudaMemoryTypeDevice:  return Storage::Device;
+  case cudaMemoryTypeManaged: return Storage::Managed;
+  default:                    return Storage::Undefined;
+  }
+}
+
+void Device::setError(Error code, const std::string& message)
+{
+  if (errorCode == Error::None)
+  {
+    errorCode = code;
+    errorMessage = message;
+  }
+  if (isVerbose(1)) fprintf(stderr, "Error: %s\n", message.c_str());
+}
+
+Error Device::getError(const char** outMessage)
+{
+  const Error c = errorCode;
+  errorMessageOut = errorMessage;
+  if (outMessage) *outMessage = c == Error::None ? nullptr : errorMessageOut.c_str();
+  errorCode = Error::None;
+  return c;
+}
+
+void Device::setGlobalError(Error code, const std::string& message)
+{
+  std::lock_guard<std::mutex> lock(g_globalMutex);
+  if (g_globalCode == Error::None) { g_globalCode = code; g_globalMessage = message; }
+}
+
+Error Device::getGlobalError(const char** outMessage)
+{
+  std::lock_guard<std::mutex> lock(g_globalMutex);
+  const Error c = g_globalCode;
+  g_globalMessageOut = g_globalMessage;
+  if (outMessage) *outMessage = c == Error::None ? nullptr : g_globalMessageOut.c_str();
+  g_globalCode = Error::None;
+  return c;
+}
+
+} // namespace oidnb200

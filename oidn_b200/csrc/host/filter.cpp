@@ -1,0 +1,667 @@
+#include "filter.hpp"
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+namespace oidnb200 {
+
+// ------------------------------------------------------------------------------------------------
+// Filter: dirty tracking (core/filter.cpp:23-86)
+// ------------------------------------------------------------------------------------------------
+void Filter::setParam(Image& dst, const Image& src)
+{
+  // The image must be dereferenceable by the GPU(s): device, managed or pinned host memory
+  if (src && !device->getInt("systemMemorySupported") && device->getPtrStorage(src.ptr) == Storage::Undefined)
+    throw Exception(Error::InvalidArgument,
+                    "image data not accessible by the device, please use OIDNBuffer or device allocator for storage");
+  // not dirty if only the pointer and/or strides change (except to/from nullptr)
+  dirtyParam |= (!dst && src) || (dst && !src) ||
+                (dst && src && (dst.W != src.W || dst.H != src.H || dst.format != src.format));
+  dst = src ? src : Image();
+}
+
+void Filter::setParam(Data& dst, const Data& src)
+{
+  if (src && device->getPtrStorage(src.ptr) == Storage::Device)
+    throw Exception(Error::InvalidArgument, "the specified data is not accessible to the host, please use host malloc");
+  dirtyParam = bool(dst) || bool(src);
+  dst = src;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile planner (core/unet_filter.cpp:254-335) and tile rectangles (:198-241)
+// ------------------------------------------------------------------------------------------------
+TilePlan planTiles(int H, int W, bool largeModel, int deviceMinAlignment, int numEngines, long maxTilePixels,
+                   const std::function<bool(const TilePlan&)>& fits)
+{
+  constexpr int minAlign = 16;
+  TilePlan p;
+  p.H = H; p.W = W;
+  const int receptiveField = largeModel ? 202 : 174;
+  p.tileAlignment = lcm_(minAlign, std::max(deviceMinAlignment, 1));
+  p.tileOverlap = round_up(receptiveField / 2, p.tileAlignment);
+  p.tileH = round_up(H, minAlign);
+  p.tileW = round_up(W, minAlign);
+  p.tilePadH = p.tileH % p.tileAlignment;
+  p.tilePadW = p.tileW % p.tileAlignment;
+  p.tileCountH = p.tileCountW = 1;
+
+  const int minTileDim = std::max(4 * p.tileOverlap, 768);
+  const int minTileH = round_up(minTileDim, p.tileAlignment, p.tilePadH);
+  const int minTileW = round_up(minTileDim, p.tileAlignment, p.tilePadW);
+  const int ovH = 2 * p.tileOverlap + p.tilePadH, ovW = 2 * p.tileOverlap + p.tilePadW;
+
+  while ((p.tileCountH * p.tileCountW) % numEngines != 0 || (long)p.tileH * p.tileW > maxTilePixels || !fits(p))
+  {
+    if (p.tileH > minTileH && p.tileH > p.tileW)
+    {
+      const int newTileH = ceil_div(H + ovH * p.tileCountH, p.tileCountH + 1);
+      p.tileH = clamp_(round_up(newTileH, p.tileAlignment, p.tilePadH), minTileH, p.tileH - p.tileAlignment);
+      p.tileCountH = std::max(ceil_div(H - ovH, p.tileH - ovH), 1);
+    }
+    else if (p.tileW > minTileW)
+    {
+      const int newTileW = ceil_div(W + ovW * p.tileCountW, p.tileCountW + 1);
+      p.tileW = clamp_(round_up(newTileW, p.tileAlignment, p.tilePadW), minTileW, p.tileW - p.tileAlignment);
+      p.tileCountW = std::max(ceil_div(W - ovW, p.tileW - ovW), 1);
+    }
+    else
+      break; // cannot divide further; the caller builds the model without a memory limit
+  }
+  return p;
+}
+
+std::vector<TileRect> enumerateTiles(const TilePlan& p)
+{
+  std::vector<TileRect> out;
+  const int ovH = 2 * p.tileOverlap + p.tilePadH, ovW = 2 * p.tileOverlap + p.tilePadW;
+  for (int i = 0; i < p.tileCountH; ++i)
+  {
+    const int h = i * (p.tileH - ovH);
+    const int obH = i > 0 ? p.tileOverlap : 0;
+    const int oeH = i < p.tileCountH - 1 ? p.tileOverlap + p.tilePadH : 0;
+    const int H1 = std::min(p.H - h, p.tileH), H2 = H1 - obH - oeH;
+    const int alignH = p.tileH - round_up(H1, 16); // bottom-aligned: keeps the 16-px pooling grid
+    for (int j = 0; j < p.tileCountW; ++j)
+    {
+      const int w = j * (p.tileW - ovW);
+      const int obW = j > 0 ? p.tileOverlap : 0;
+      const int oeW = j < p.tileCountW - 1 ? p.tileOverlap + p.tilePadW : 0;
+      const int W1 = std::min(p.W - w, p.tileW), W2 = W1 - obW - oeW;
+      const int alignW = p.tileW - round_up(W1, 16);
+      out.push_back(TileRect{h, w, alignH, alignW, H1, W1, alignH + obH, alignW + obW, h + obH, w + obW, H2, W2});
+    }
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// UNetFilter
+// ------------------------------------------------------------------------------------------------
+UNetFilter::UNetFilter(Device* device) : Filter(device), inputScale(std::numeric_limits<float>::quiet_NaN()) {}
+
+UNetFilter::~UNetFilter()
+{
+  try { device->wait(); } catch (...) {}
+  cleanup();
+}
+
+static void warnUnknown(Device* device, const std::string& name)
+{
+  if (device->isVerbose(1))
+    std::cerr << "Warning: unknown filter parameter or type mismatch: '" << name << "'" << std::endl;
+}
+
+void UNetFilter::setData(const std::string& name, const Data& data)
+{
+  if (name == "weights") setParam(userWeightsBlob, data); else warnUnknown(device, name);
+  dirty = true;
+}
+
+void UNetFilter::updateData(const std::string& name)
+{
+  if (name == "weights") dirtyParam |= bool(userWeightsBlob); else warnUnknown(device, name);
+  dirty = true;
+}
+
+void UNetFilter::unsetData(const std::string& name)
+{
+  if (name == "weights") removeParam(userWeightsBlob); else warnUnknown(device, name);
+  dirty = true;
+}
+
+void UNetFilter::setInt(const std::string& name, int value)
+{
+  if (name == "quality")
+  {
+    Quality q = static_cast<Quality>(value);
+    if (q == Quality::Default) q = defaultQuality;
+    else if (q != Quality::High && q != Quality::Balanced && q != Quality::Fast)
+      throw Exception(Error::InvalidArgument, "unknown filter quality mode");
+    setParam(quality, q);
+  }
+  else if (name == "maxMemoryMB") setParam(maxMemoryMB, value);
+  else warnUnknown(device, name);
+  dirty = true;
+}
+
+int UNetFilter::getInt(const std::string& name)
+{
+  if (name == "quality") return static_cast<int>(quality);
+  if (name == "maxMemoryMB") return maxMemoryMB;
+  if (name == "tileAlignment" || name == "alignment") return plan.tileAlignment;
+  if (name == "tileOverlap" || name == "overlap") return plan.tileOverlap;
+  throw Exception(Error::InvalidArgument, "unknown filter parameter or type mismatch: '" + name + "'");
+}
+
+void UNetFilter::setFloat(const std::string& name, float value)
+{
+  if (name == "inputScale" || name == "hdrScale") inputScale = value; else warnUnknown(device, name);
+  dirty = true;
+}
+
+float UNetFilter::getFloat(const std::string& name)
+{
+  if (name == "inputScale" || name == "hdrScale") return inputScale;
+  throw Exception(Error::InvalidArgument, "unknown filter parameter or type mismatch: '" + name + "'");
+}
+
+void UNetFilter::commit()
+{
+  if (!dirty) return;
+  const bool inplaceNew = output && ((color && output.overlaps(color)) || (albedo && output.overlaps(albedo)) ||
+                                     (normal && output.overlaps(normal)));
+  setParam(inplaceParam, (int)inplaceNew);
+  inplace = inplaceNew;
+  if (dirtyParam)
+  {
+    device->wait(); // all asynchronous work must have completed before the model is rebuilt
+    init();
+  }
+  dirty = false;
+  dirtyParam = false;
+}
+
+void UNetFilter::cleanup()
+{
+  freeScratch();
+  instances.clear();
+  transferFunc.reset();
+  autoexposure.reset();
+  imageCopy.reset();
+  outputTemp = Image();
+  tiles.clear();
+}
+
+void UNetFilter::freeScratch()
+{
+  for (size_t i = 0; i < instances.size(); ++i)
+    if (instances[i].scratch)
+    {
+      device->getEngine((int)i)->free(instances[i].scratch);
+      instances[i].scratch = nullptr;
+    }
+}
+
+void UNetFilter::checkParams()
+{
+  if (!color && !albedo && !normal) throw Exception(Error::InvalidOperation, "input image not specified");
+  if (!output) throw Exception(Error::InvalidOperation, "output image not specified");
+  auto supported = [](Format f) {
+    return f == Format::Float3 || f == Format::Half3 || f == Format::Float2 || f == Format::Half2 ||
+           f == Format::Float || f == Format::Half;
+  };
+  if ((color && !supported(color.format)) || (albedo && !supported(albedo.format)) || (normal && !supported(normal.format)))
+    throw Exception(Error::InvalidOperation, "unsupported input image format");
+  if (!supported(output.format)) throw Exception(Error::InvalidOperation, "unsupported output image format");
+  const Image& input = color ? color : (albedo ? albedo : normal);
+  if (input.C() != output.C()) throw Exception(Error::InvalidOperation, "input/output image channel count mismatch");
+  if ((color && (color.W != output.W || color.H != output.H)) || (albedo && (albedo.W != output.W || albedo.H != output.H)) ||
+      (normal && (normal.W != output.W || normal.H != output.H)))
+    throw Exception(Error::InvalidOperation, "image size mismatch");
+  if (directional && (hdr || srgb))
+    throw Exception(Error::InvalidOperation, "directional and hdr/srgb modes cannot be enabled at the same time");
+  if (hdr && srgb) throw Exception(Error::InvalidOperation, "hdr and srgb modes cannot be enabled at the same time");
+}
+
+// Reads <weightsDir>/<stem>.tza; a missing file or a Git-LFS pointer counts as "model not available".
+static std::shared_ptr<std::vector<uint8_t>> loadModelFile(const std::string& dir, const char* stem)
+{
+  if (!stem || dir.empty()) return nullptr;
+  std::ifstream f(dir + "/" + stem + ".tza", std::ios::binary);
+  if (!f) return nullptr;
+  auto blob = std::make_shared<std::vector<uint8_t>>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  if (blob->size() < 12 || memcmp(blob->data(), "version ", 8) == 0) return nullptr;
+  return blob;
+}
+
+Data UNetFilter::getWeights()
+{
+  // model slot: core/unet_filter.cpp:394-441
+  Model* model = nullptr;
+  if (color)
+  {
+    if (!albedo && !normal) model = directional ? &models.dir : (hdr ? &models.hdr : &models.ldr);
+    else if (albedo && !normal) model = hdr ? &models.hdr_alb : &models.ldr_alb;
+    else if (albedo && normal)
+    {
+      if (cleanAux) model = hdr ? &models.hdr_calb_cnrm : &models.ldr_calb_cnrm;
+      else model = hdr ? &models.hdr_alb_nrm : &models.ldr_alb_nrm;
+    }
+  }
+  else
+  {
+    if (albedo && !normal)
+    {
+      if (hdr) throw Exception(Error::InvalidOperation, "hdr mode is not supported for albedo filtering");
+      model = &models.alb;
+    }
+    else if (!albedo && normal)
+    {
+      if (hdr || srgb) throw Exception(Error::InvalidOperation, "hdr and srgb modes are not supported for normal filtering");
+      model = &models.nrm;
+    }
+    else
+      throw Exception(Error::InvalidOperation, "invalid combination of input features");
+  }
+
+  if (userWeightsBlob) return userWeightsBlob;
+
+  // quality -> variant with the reference's fallbacks (core/unet_filter.cpp:451-463)
+  builtinBlob.reset();
+  if (model)
+  {
+    const std::string& dir = device->getWeightsDir();
+    auto pick = [&](const char* first, const char* second) {
+      auto b = loadModelFile(dir, first);
+      return b ? b : loadModelFile(dir, second);
+    };
+    switch (quality)
+    {
+    case Quality::Default:
+    case Quality::High:     builtinBlob = pick(model->large, model->base); break;
+    case Quality::Balanced: builtinBlob = loadModelFile(dir, model->base); break;
+    case Quality::Fast:     builtinBlob = pick(model->small, model->base); break;
+    }
+  }
+  if (!builtinBlob) throw Exception(Error::InvalidOperation, "unsupported combination of input features");
+  Data d;
+  d.ptr = builtinBlob->data();
+  d.size = builtinBlob->size();
+  return d;
+}
+
+Graph::Value UNetFilter::addUNet(Graph& g, Graph::Value input)
+{
+  // core/unet_filter.cpp:468-498 == training/model.py:55-155
+  auto x = g.addConv("enc_conv0", input, Activation::ReLU);
+  auto pool1 = x = g.addConv("enc_conv1", x, Activation::ReLU, PostOp::Pool);
+  auto pool2 = x = g.addConv("enc_conv2", x, Activation::ReLU, PostOp::Pool);
+  auto pool3 = x = g.addConv("enc_conv3", x, Activation::ReLU, PostOp::Pool);
+  auto pool4 = x = g.addConv("enc_conv4", x, Activation::ReLU, PostOp::Pool);
+  x = g.addConv("enc_conv5a", pool4, Activation::ReLU);
+  x = g.addConv("enc_conv5b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv4a", x, pool3, Activation::ReLU);
+  x = g.addConv("dec_conv4b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv3a", x, pool2, Activation::ReLU);
+  x = g.addConv("dec_conv3b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv2a", x, pool1, Activation::ReLU);
+  x = g.addConv("dec_conv2b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv1a", x, input, Activation::ReLU);
+  x = g.addConv("dec_conv1b", x, Activation::ReLU);
+  x = g.addConv("dec_conv0", x, Activation::ReLU);
+  return x;
+}
+
+Graph::Value UNetFilter::addUNetLarge(Graph& g, Graph::Value input)
+{
+  // core/unet_filter.cpp:500-531 == training/model.py:161-260
+  auto x = g.addConv("enc_conv1a", input, Activation::ReLU);
+  auto pool1 = x = g.addConv("enc_conv1b", x, Activation::ReLU, PostOp::Pool);
+  x = g.addConv("enc_conv2a", x, Activation::ReLU);
+  auto pool2 = x = g.addConv("enc_conv2b", x, Activation::ReLU, PostOp::Pool);
+  x = g.addConv("enc_conv3a", x, Activation::ReLU);
+  auto pool3 = x = g.addConv("enc_conv3b", x, Activation::ReLU, PostOp::Pool);
+  x = g.addConv("enc_conv4a", x, Activation::ReLU);
+  auto pool4 = x = g.addConv("enc_conv4b", x, Activation::ReLU, PostOp::Pool);
+  x = g.addConv("enc_conv5a", pool4, Activation::ReLU);
+  x = g.addConv("enc_conv5b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv4a", x, pool3, Activation::ReLU);
+  x = g.addConv("dec_conv4b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv3a", x, pool2, Activation::ReLU);
+  x = g.addConv("dec_conv3b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv2a", x, pool1, Activation::ReLU);
+  x = g.addConv("dec_conv2b", x, Activation::ReLU, PostOp::Upsample);
+  x = g.addConcatConv("dec_conv1a", x, input, Activation::ReLU);
+  x = g.addConv("dec_conv1b", x, Activation::ReLU);
+  x = g.addConv("dec_conv1c", x, Activation::ReLU);
+  return x;
+}
+
+// Builds one graph per engine for the candidate tile size. Returns false if the memory estimate
+// exceeds maxMemoryByteSize (core/unet_filter.cpp:534-653). With commitModel the scratch buffers
+// are allocated and the graphs finalized.
+bool UNetFilter::buildModel(const TilePlan& cand, size_t maxMemoryByteSize, bool commitModel)
+{
+  freeScratch();
+  instances.clear();
+  autoexposure.reset();
+  imageCopy.reset();
+  outputTemp = Image();
+  if (cand.H <= 0 || cand.W <= 0) return true;
+
+  int inputC = 0;
+  if (color) inputC += 3; // always broadcast to 3 channels
+  if (albedo) inputC += 3;
+  if (normal) inputC += 3;
+  const bool snorm = directional || (!color && normal);
+  const int numEngines = device->getNumEngines();
+
+  if (hdr) autoexposure = device->getEngine(0)->newAutoexposure(color.H, color.W);
+
+  size_t outputTempOffset = SIZE_MAX, autoexposureDstOffset = SIZE_MAX;
+  for (int id = 0; id < numEngines; ++id)
+  {
+    Engine* engine = device->getEngine(id);
+    instances.emplace_back();
+    Instance& inst = instances.back();
+    inst.graph.reset(new Graph(engine, constTensors));
+    Graph& g = *inst.graph;
+    auto in = g.addInputProcess("input", TensorDesc{inputC, cand.tileH, cand.tileW}, transferFunc, hdr, snorm);
+    auto x = largeModel ? addUNetLarge(g, in) : addUNet(g, in);
+    g.addOutputProcess("output", x, transferFunc, hdr, snorm);
+
+    const size_t graphScratch = round_up(g.getScratchByteSize(), memoryAlignment);
+    size_t scratch = graphScratch;
+    if (id == 0 && hdr) scratch = round_up(std::max(scratch, autoexposure->getScratchByteSize()), memoryAlignment);
+    if (id == 0 && inplace && cand.tileCountH * cand.tileCountW > 1)
+    {
+      outputTempOffset = scratch;
+      scratch += round_up((size_t)output.W * output.H * formatBytes(output.format), memoryAlignment);
+    }
+    if (id == 0 && hdr)
+    {
+      autoexposureDstOffset = scratch;
+      scratch += round_up(sizeof(float), memoryAlignment);
+    }
+    inst.scratchByteSize = scratch;
+    if (id == 0)
+    {
+      totalMemoryByteSize = (scratch + g.getPrivateByteSize()) + (graphScratch + g.getPrivateByteSize()) * (size_t)(numEngines - 1);
+      if (totalMemoryByteSize > maxMemoryByteSize)
+      {
+        instances.clear();
+        return false;
+      }
+    }
+  }
+  if (!commitModel) return true;
+
+  for (int id = 0; id < numEngines; ++id)
+  {
+    Instance& inst = instances[id];
+    inst.scratch = device->getEngine(id)->malloc(inst.scratchByteSize);
+    inst.graph->setScratch(inst.scratch, inst.scratchByteSize);
+    inst.graph->finalize();
+    inst.inputProcess = inst.graph->getInputProcess();
+    inst.outputProcess = inst.graph->getOutputProcess();
+  }
+  uint8_t* s0 = static_cast<uint8_t*>(instances[0].scratch);
+  if (hdr)
+  {
+    autoexposure->setScratch(s0);
+    autoexposure->setDst(reinterpret_cast<float*>(s0 + autoexposureDstOffset));
+  }
+  if (outputTempOffset != SIZE_MAX)
+  {
+    outputTemp = output;
+    outputTemp.ptr = s0 + outputTempOffset;
+    outputTemp.pixelStride = formatBytes(output.format);
+    outputTemp.rowStride = outputTemp.pixelStride * output.W;
+    imageCopy = device->getEngine(0)->newImageCopy();
+    imageCopy->setSrc(outputTemp);
+  }
+  return true;
+}
+
+void UNetFilter::init()
+{
+  cleanup();
+  checkParams();
+
+  const Data weights = getWeights();
+  constTensors = parseTZA(weights.ptr, weights.size);
+  largeModel = constTensors->find("enc_conv1b.weight") != constTensors->end();
+  transferFunc = newTransferFunc();
+
+  const int H = output.H, W = output.W;
+  const long maxTilePixels = maxMemoryMB < 0 ? device->getMaxTilePixels() : LONG_MAX;
+  const size_t maxMemoryByteSize = maxMemoryMB >= 0 ? (size_t)maxMemoryMB * 1024 * 1024 : SIZE_MAX;
+
+  plan = planTiles(H, W, largeModel, device->getMinTileAlignment(), device->getNumEngines(), maxTilePixels,
+                   [&](const TilePlan& c) { return buildModel(c, maxMemoryByteSize, false); });
+  if (!buildModel(plan, SIZE_MAX, true)) throw std::runtime_error("could not build filter model");
+  tiles = enumerateTiles(plan);
+
+  if (device->isVerbose(2))
+  {
+    std::cout << "Image size: " << W << "x" << H << std::endl;
+    std::cout << "Tile size : " << plan.tileW << "x" << plan.tileH << std::endl;
+    std::cout << "Tile count: " << plan.tileCountW << "x" << plan.tileCountH << std::endl;
+    std::cout << "In-place  : " << (inplace ? "true" : "false") << std::endl;
+    std::cout << "Memory usage: " << totalMemoryByteSize << std::endl;
+  }
+}
+
+namespace {
+struct ProgressState
+{
+  ProgressMonitorFunction func;
+  void* userPtr;
+  double total;
+  std::atomic<double> done{0};
+  std::atomic<bool> cancelled{false};
+  void update(double amount)
+  {
+    if (cancelled) return;
+    const double d = done.load() + amount;
+    done.store(d);
+    if (!func(userPtr, std::min(d / total, 1.0))) cancelled = true;
+  }
+};
+} // namespace
+
+void UNetFilter::execute(SyncMode sync)
+{
+  if (dirty) throw Exception(Error::InvalidOperation, "changes to the filter are not committed");
+  if (plan.H <= 0 || plan.W <= 0) return;
+  const int numEngines = device->getNumEngines();
+
+  // Progress: one unit per tile (+1 for autoexposure, +1 for the final copy), reported from
+  // host callbacks in stream order (core/progress.cpp:17-39 reports per op; per tile here).
+  std::shared_ptr<ProgressState> progress;
+  if (progressFunc)
+  {
+    progress = std::make_shared<ProgressState>();
+    progress->func = progressFunc; progress->userPtr = progressUserPtr;
+    progress->total = (double)tiles.size() + ((hdr && std::isnan(inputScale)) ? 1 : 0) + (outputTemp ? 1 : 0);
+    if (!progressFunc(progressUserPtr, 0.)) throw Exception(Error::Cancelled, "execution was cancelled");
+  }
+  auto report = [&](Engine* e) {
+    if (progress) { auto p = progress; e->submitHostFunc([p]() { p->update(1.); }); }
+  };
+  auto checkCancel = [&]() {
+    if (progress && progress->cancelled)
+    {
+      device->wait();
+      throw Exception(Error::Cancelled, "execution was cancelled");
+    }
+  };
+
+  // input scale (core/unet_filter.cpp:172-189)
+  if (std::isnan(inputScale))
+  {
+    if (hdr)
+    {
+      autoexposure->setSrc(color);
+      device->getEngine(0)->makeCurrent();
+      autoexposure->submit();
+      report(device->getEngine(0));
+      device->submitBarrier();
+      transferFunc->setInputScale(autoexposure->getDstPtr());
+    }
+    else
+      transferFunc->setInputScale(1.f);
+  }
+  else
+    transferFunc->setInputScale(inputScale);
+
+  for (auto& inst : instances)
+  {
+    inst.inputProcess->setSrc(color, albedo, normal);
+    inst.outputProcess->setDst(outputTemp ? outputTemp : output);
+  }
+
+  int tileIndex = 0;
+  for (const TileRect& t : tiles)
+  {
+    checkCancel();
+    Instance& inst = instances[tileIndex % numEngines];
+    inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
+    inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
+    inst.graph->submit();
+    report(device->getEngine(tileIndex % numEngines));
+    ++tileIndex;
+  }
+  device->submitBarrier();
+
+  if (outputTemp)
+  {
+    device->getEngine(0)->makeCurrent();
+    imageCopy->setDst(output);
+    imageCopy->submit();
+    report(device->getEngine(0));
+  }
+
+  if (sync == SyncMode::Blocking || progress)
+  {
+    device->wait();
+    if (progress && progress->cancelled) throw Exception(Error::Cancelled, "execution was cancelled");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RTFilter (core/rt_filter.cpp)
+// ------------------------------------------------------------------------------------------------
+RTFilter::RTFilter(Device* device) : UNetFilter(device)
+{
+  // weight file stems = the reference's blob names (CMakeLists.txt:55-86, core/rt_filter.cpp:34-60)
+  models.hdr           = {"rt_hdr", "rt_hdr_small", nullptr};
+  models.hdr_alb       = {"rt_hdr_alb", "rt_hdr_alb_small", nullptr};
+  models.hdr_alb_nrm   = {"rt_hdr_alb_nrm", "rt_hdr_alb_nrm_small", nullptr};
+  models.hdr_calb_cnrm = {"rt_hdr_calb_cnrm", "rt_hdr_calb_cnrm_small", "rt_hdr_calb_cnrm_large"};
+  models.ldr           = {"rt_ldr", "rt_ldr_small", nullptr};
+  models.ldr_alb       = {"rt_ldr_alb", "rt_ldr_alb_small", nullptr};
+  models.ldr_alb_nrm   = {"rt_ldr_alb_nrm", "rt_ldr_alb_nrm_small", nullptr};
+  models.ldr_calb_cnrm = {"rt_ldr_calb_cnrm", "rt_ldr_calb_cnrm_small", nullptr};
+  models.alb           = {"rt_alb", nullptr, "rt_alb_large"};
+  models.nrm           = {"rt_nrm", nullptr, "rt_nrm_large"};
+}
+
+std::shared_ptr<TransferFunction> RTFilter::newTransferFunc()
+{
+  if (srgb || (!color && normal)) return std::make_shared<TransferFunction>(TransferType::Linear);
+  if (hdr) return std::make_shared<TransferFunction>(TransferType::PU);
+  return std::make_shared<TransferFunction>(TransferType::SRGB);
+}
+
+void RTFilter::setImage(const std::string& name, const Image& image)
+{
+  if (name == "color") setParam(color, image);
+  else if (name == "albedo") setParam(albedo, image);
+  else if (name == "normal") setParam(normal, image);
+  else if (name == "output") setParam(output, image);
+  else warnUnknown(device, name);
+  dirty = true;
+}
+
+void RTFilter::unsetImage(const std::string& name)
+{
+  if (name == "color") removeParam(color);
+  else if (name == "albedo") removeParam(albedo);
+  else if (name == "normal") removeParam(normal);
+  else if (name == "output") removeParam(output);
+  else warnUnknown(device, name);
+  dirty = true;
+}
+
+void RTFilter::setInt(const std::string& name, int value)
+{
+  if (name == "hdr") setParam(hdr, value);
+  else if (name == "srgb") setParam(srgb, value);
+  else if (name == "cleanAux") setParam(cleanAux, value);
+  else UNetFilter::setInt(name, value);
+  dirty = true;
+}
+
+int RTFilter::getInt(const std::string& name)
+{
+  if (name == "hdr") return hdr;
+  if (name == "srgb") return srgb;
+  if (name == "cleanAux") return cleanAux;
+  return UNetFilter::getInt(name);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RTLightmapFilter (core/rtlightmap_filter.cpp)
+// ------------------------------------------------------------------------------------------------
+RTLightmapFilter::RTLightmapFilter(Device* device) : UNetFilter(device)
+{
+  hdr = true; // core/rtlightmap_filter.cpp:14
+  models.hdr = {"rtlightmap_hdr", nullptr, nullptr};
+  models.dir = {"rtlightmap_dir", nullptr, nullptr};
+}
+
+std::shared_ptr<TransferFunction> RTLightmapFilter::newTransferFunc()
+{
+  return std::make_shared<TransferFunction>(hdr ? TransferType::Log : TransferType::Linear);
+}
+
+void RTLightmapFilter::setImage(const std::string& name, const Image& image)
+{
+  if (name == "color") setParam(color, image);
+  else if (name == "output") setParam(output, image);
+  else warnUnknown(device, name);
+  dirty = true;
+}
+
+void RTLightmapFilter::unsetImage(const std::string& name)
+{
+  if (name == "color") removeParam(color);
+  else if (name == "output") removeParam(output);
+  else warnUnknown(device, name);
+  dirty = true;
+}
+
+void RTLightmapFilter::setInt(const std::string& name, int value)
+{
+  if (name == "directional")
+  {
+    setParam(directional, value);
+    hdr = !directional; // core/rtlightmap_filter.cpp:58-62
+  }
+  else UNetFilter::setInt(name, value);
+  dirty = true;
+}
+
+int RTLightmapFilter::getInt(const std::string& name)
+{
+  if (name == "directional") return directional;
+  return UNetFilter::getInt(name);
+}
+
+} // namespace oidnb200

@@ -1,0 +1,194 @@
+// Filters: the parameter surface, model selection, tile/overlap scheduler and per-frame execute
+// loop of the reference's UNet filters, rebuilt for the B200 engine.
+//   Filter            core/filter.h:12-40, core/filter.cpp:23-86 (dirty tracking)
+//   UNetFilter        core/unet_filter.{h,cpp} (params :43-113, commit :115-143, execute :145-252,
+//                     tile planner :254-335, checkParams :346-392, model choice :394-466,
+//                     topology :468-531, buildModel :534-653)
+//   RTFilter          core/rt_filter.cpp:31-129
+//   RTLightmapFilter  core/rtlightmap_filter.cpp:11-75
+#pragma once
+#include "device.hpp"
+#include "graph.hpp"
+
+namespace oidnb200 {
+
+typedef bool (*ProgressMonitorFunction)(void* userPtr, double n);
+
+struct Data
+{
+  const void* ptr = nullptr;
+  size_t size = 0;
+  explicit operator bool() const { return ptr != nullptr; }
+};
+
+class Filter
+{
+public:
+  explicit Filter(Device* device) : device(device) {}
+  virtual ~Filter() = default;
+
+  virtual void setImage(const std::string& name, const Image& image) = 0;
+  virtual void unsetImage(const std::string& name) = 0;
+  virtual void setData(const std::string& name, const Data& data) = 0;
+  virtual void updateData(const std::string& name) = 0;
+  virtual void unsetData(const std::string& name) = 0;
+  virtual void setInt(const std::string& name, int value) = 0;
+  virtual int getInt(const std::string& name) = 0;
+  virtual void setFloat(const std::string& name, float value) = 0;
+  virtual float getFloat(const std::string& name) = 0;
+  virtual void commit() = 0;
+  virtual void execute(SyncMode sync) = 0;
+
+  void setProgressMonitorFunction(ProgressMonitorFunction func, void* userPtr) { progressFunc = func; progressUserPtr = userPtr; }
+  Device* getDevice() const { return device; }
+
+protected:
+  // set a parameter and track whether the model must be rebuilt
+  void setParam(int& dst, int src) { dirtyParam |= dst != src; dst = src; }
+  void setParam(bool& dst, int src) { dirtyParam |= dst != (src != 0); dst = src != 0; }
+  void setParam(Quality& dst, Quality src) { dirtyParam |= dst != src; dst = src; }
+  void setParam(Image& dst, const Image& src);
+  void removeParam(Image& dst) { dirtyParam |= bool(dst); dst = Image(); }
+  void setParam(Data& dst, const Data& src);
+  void removeParam(Data& dst) { dirtyParam |= bool(dst); dst = Data(); }
+
+  Device* device;
+  ProgressMonitorFunction progressFunc = nullptr;
+  void* progressUserPtr = nullptr;
+  bool dirty = true;
+  bool dirtyParam = true;
+};
+
+// Tile grid (also exposed to tests through the C API)
+struct TilePlan
+{
+  int H = 0, W = 0;
+  int tileH = 0, tileW = 0, tilePadH = 0, tilePadW = 0;
+  int tileCountH = 1, tileCountW = 1;
+  int tileAlignment = 16, tileOverlap = 0;
+};
+
+struct TileRect
+{
+  // input tile: source origin in the image, origin in the tile buffer, size (incl. overlaps)
+  int hSrc, wSrc, hBuf, wBuf, H1, W1;
+  // output tile: origin in the tile buffer, origin in the image, size
+  int hOutBuf, wOutBuf, hDst, wDst, H2, W2;
+};
+
+// Shrinks tiles until numTiles % numEngines == 0, tile pixels <= maxTilePixels and fits(plan).
+// Same search as core/unet_filter.cpp:283-326. `fits` is the memory test (buildModel).
+TilePlan planTiles(int H, int W, bool largeModel, int deviceMinAlignment, int numEngines, long maxTilePixels,
+                   const std::function<bool(const TilePlan&)>& fits);
+std::vector<TileRect> enumerateTiles(const TilePlan& plan);
+
+class UNetFilter : public Filter
+{
+public:
+  explicit UNetFilter(Device* device);
+  ~UNetFilter() override;
+
+  void setData(const std::string& name, const Data& data) override;
+  void updateData(const std::string& name) override;
+  void unsetData(const std::string& name) override;
+  void setInt(const std::string& name, int value) override;
+  int getInt(const std::string& name) override;
+  void setFloat(const std::string& name, float value) override;
+  float getFloat(const std::string& name) override;
+  void commit() override;
+  void execute(SyncMode sync) override;
+
+  const TilePlan& getTilePlan() const { return plan; }
+  bool isLargeModel() const { return largeModel; }
+  size_t getScratchByteSize() const { return totalMemoryByteSize; }
+
+protected:
+  virtual std::shared_ptr<TransferFunction> newTransferFunc() = 0;
+
+  static constexpr int minTileAlignment = 16;       // core/unet_filter.h:35-39
+  static constexpr int receptiveFieldBase = 174;
+  static constexpr int receptiveFieldLarge = 202;
+  static constexpr Quality defaultQuality = Quality::High;
+
+  // Built-in model slots (core/unet_filter.h). A slot is a weights file name stem; the blob is
+  // loaded from the device's weights directory on demand. The reference compiles these blobs in;
+  // its weights submodule is Git-LFS pointers in this checkout, so they are looked up at run time.
+  struct Model
+  {
+    const char* base = nullptr;
+    const char* small = nullptr;
+    const char* large = nullptr;
+  };
+  struct
+  {
+    Model hdr, hdr_alb, hdr_alb_nrm, hdr_calb_cnrm;
+    Model ldr, ldr_alb, ldr_alb_nrm, ldr_calb_cnrm;
+    Model dir, alb, nrm;
+  } models;
+
+  Image color, albedo, normal, output;
+  Image outputTemp;
+  bool hdr = false, srgb = false, directional = false, cleanAux = false;
+  float inputScale;
+  Quality quality = defaultQuality;
+  int maxMemoryMB = -1;
+
+private:
+  void init();
+  void cleanup();
+  void checkParams();
+  Data getWeights();
+  Graph::Value addUNet(Graph& graph, Graph::Value input);
+  Graph::Value addUNetLarge(Graph& graph, Graph::Value input);
+  bool buildModel(const TilePlan& candidate, size_t maxMemoryByteSize, bool commitModel);
+  void freeScratch();
+
+  struct Instance
+  {
+    std::unique_ptr<Graph> graph;
+    std::shared_ptr<InputProcess> inputProcess;
+    std::shared_ptr<OutputProcess> outputProcess;
+    void* scratch = nullptr;
+    size_t scratchByteSize = 0;
+  };
+
+  Data userWeightsBlob;
+  std::shared_ptr<std::vector<uint8_t>> builtinBlob; // keeps a file-loaded model alive
+  std::shared_ptr<TensorMap> constTensors;
+  std::vector<Instance> instances;
+  std::shared_ptr<TransferFunction> transferFunc;
+  std::shared_ptr<Autoexposure> autoexposure;
+  std::shared_ptr<ImageCopy> imageCopy;
+  std::vector<TileRect> tiles;
+  TilePlan plan;
+  bool largeModel = false;
+  bool inplace = false;
+  int inplaceParam = 0;
+  size_t totalMemoryByteSize = 0;
+};
+
+class RTFilter final : public UNetFilter
+{
+public:
+  explicit RTFilter(Device* device);
+  void setImage(const std::string& name, const Image& image) override;
+  void unsetImage(const std::string& name) override;
+  void setInt(const std::string& name, int value) override;
+  int getInt(const std::string& name) override;
+protected:
+  std::shared_ptr<TransferFunction> newTransferFunc() override;
+};
+
+class RTLightmapFilter final : public UNetFilter
+{
+public:
+  explicit RTLightmapFilter(Device* device);
+  void setImage(const std::string& name, const Image& image) override;
+  void unsetImage(const std::string& name) override;
+  void setInt(const std::string& name, int value) override;
+  int getInt(const std::string& name) override;
+protected:
+  std::shared_ptr<TransferFunction> newTransferFunc() override;
+};
+
+} // namespace oidnb200

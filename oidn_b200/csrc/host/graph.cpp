@@ -1,0 +1,198 @@
+#include "graph.hpp"
+#include "../kernels/common.h"
+#include <cuda_runtime.h>
+#include <cstring>
+
+namespace oidnb200 {
+
+Graph::Graph(Engine* engine, std::shared_ptr<TensorMap> constTensors)
+  : engine(engine), constTensors(std::move(constTensors)) {}
+
+Graph::~Graph() { clear(); }
+
+void Graph::clear()
+{
+  ops.clear(); nodes.clear(); convs.clear();
+  inputProcess.reset(); outputProcess.reset();
+  inputNode = outputSrcNode = -1;
+  planner.clear();
+  planned = finalized = false;
+  privateByteSize = 0;
+  if (weightBuffer) { engine->free(weightBuffer); weightBuffer = nullptr; }
+}
+
+const ConstTensor& Graph::findConst(const std::string& name) const
+{
+  auto it = constTensors->find(name);
+  if (it == constTensors->end()) throw std::invalid_argument("weights blob has no tensor named '" + name + "'");
+  return it->second;
+}
+
+TensorDesc Graph::getLogicalDesc(Value v) const
+{
+  const Node& n = nodes.at(v.id);
+  return n.upsampled ? TensorDesc{n.stored.C, n.stored.H * 2, n.stored.W * 2} : n.stored;
+}
+
+Graph::Value Graph::addInputProcess(const std::string& name, const TensorDesc& dstDesc,
+                                    const std::shared_ptr<TransferFunction>& tf, bool hdr, bool snorm)
+{
+  if (finalized) throw std::logic_error("graph cannot be changed after finalization");
+  const int opID = (int)ops.size();
+  inputProcess = engine->newInputProcess(dstDesc, tf, hdr, snorm);
+  inputProcess->setName(name);
+  ops.push_back(inputProcess);
+  nodes.push_back(Node{dstDesc, false, planner.newAlloc(opID, dstDesc.byteSize()), opID});
+  inputNode = (int)nodes.size() - 1;
+  return Value{inputNode};
+}
+
+void Graph::addOutputProcess(const std::string& name, Value src, const std::shared_ptr<TransferFunction>& tf,
+                             bool hdr, bool snorm)
+{
+  if (finalized) throw std::logic_error("graph cannot be changed after finalization");
+  const Node& n = nodes.at(src.id);
+  if (n.upsampled || n.stored.C < 3) throw std::invalid_argument("invalid output process source");
+  const int opID = (int)ops.size();
+  outputProcess = engine->newOutputProcess(n.stored, tf, hdr, snorm);
+  outputProcess->setName(name);
+  ops.push_back(outputProcess);
+  planner.addDep(opID, n.allocID);
+  outputSrcNode = src.id;
+}
+
+Graph::Value Graph::addConv(const std::string& name, Value src, Activation activation, PostOp postOp)
+{
+  return addConvImpl(name, src, Value{-1}, activation, postOp);
+}
+
+Graph::Value Graph::addConcatConv(const std::string& name, Value src1, Value src2, Activation activation)
+{
+  return addConvImpl(name, src1, src2, activation, PostOp::None);
+}
+
+Graph::Value Graph::addConvImpl(const std::string& name, Value s1, Value s2, Activation activation, PostOp postOp)
+{
+  if (finalized) throw std::logic_error("graph cannot be changed after finalization");
+  const Node n1 = nodes.at(s1.id);
+  const bool concat = s2.id >= 0;
+  const TensorDesc l1 = getLogicalDesc(s1);
+  ConvDesc d;
+  d.src1 = n1.stored;
+  d.src1Upsampled = n1.upsampled;
+  d.H = l1.H; d.W = l1.W;
+  int I2 = 0;
+  if (concat)
+  {
+    const Node& n2 = nodes.at(s2.id);
+    if (n2.upsampled || n2.stored.H != l1.H || n2.stored.W != l1.W)
+      throw std::invalid_argument("invalid concat+conv source descriptor"); // core/concat_conv.cpp:17
+    d.src2 = n2.stored;
+    I2 = n2.stored.C;
+  }
+  // weights: [O, I, 3, 3] "oihw", bias [O] "x" (core/graph.cpp:82-89)
+  const ConstTensor& w = findConst(name + ".weight");
+  const ConstTensor& b = findConst(name + ".bias");
+  if (w.dims.size() != 4 || w.dims[2] != 3 || w.dims[3] != 3 || b.dims.size() != 1 || b.dims[0] != w.dims[0] ||
+      w.dims[1] != n1.stored.C + I2)
+    throw std::invalid_argument("invalid convolution weight/bias");
+  d.outC = w.dims[0];
+  d.activation = activation;
+  d.postOp = postOp;
+  if (postOp == PostOp::Pool && ((d.H & 1) || (d.W & 1)))
+    throw std::invalid_argument("invalid pooling source shape"); // core/conv.cpp:27
+
+  const int opID = (int)ops.size();
+  auto conv = engine->newConv(d);
+  conv->setName(name);
+  ops.push_back(conv);
+  const TensorDesc dst = conv->getDstDesc();
+  nodes.push_back(Node{dst, postOp == PostOp::Upsample, planner.newAlloc(opID, dst.byteSize()), opID});
+  planner.addDep(opID, n1.allocID);
+  if (concat) planner.addDep(opID, nodes.at(s2.id).allocID);
+
+  ConvRecord r;
+  r.conv = conv; r.src1 = s1.id; r.src2 = s2.id; r.dst = (int)nodes.size() - 1;
+  r.weight = &w; r.bias = &b; r.I1 = n1.stored.C; r.I2 = I2;
+  r.weightOffset = round_up(privateByteSize, memoryAlignment);
+  r.biasOffset = round_up(r.weightOffset + conv->getWeightByteSize(), memoryAlignment);
+  privateByteSize = r.biasOffset + conv->getBiasByteSize();
+  convs.push_back(r);
+  planned = false;
+  return Value{r.dst};
+}
+
+size_t Graph::getScratchByteSize()
+{
+  if (!planned)
+  {
+    planner.commit();
+    planned = true;
+  }
+  return planner.getByteSize();
+}
+
+void Graph::setScratch(void* base, size_t byteSize)
+{
+  if (byteSize < getScratchByteSize()) throw std::invalid_argument("graph scratch buffer is too small");
+  scratchBase = base;
+  scratchSize = byteSize;
+  finalized = false;
+}
+
+static std::vector<uint16_t> asHalfBits(const ConstTensor& t)
+{
+  std::vector<uint16_t> out(t.count());
+  if (t.dtype == 'h')
+    memcpy(out.data(), t.data, out.size() * 2);
+  else
+  {
+    const float* f = static_cast<const float*>(t.data);
+    for (size_t i = 0; i < out.size(); ++i) out[i] = float_to_half_bits(f[i]);
+  }
+  return out;
+}
+
+void Graph::finalize()
+{
+  if (!scratchBase && getScratchByteSize() > 0) throw std::logic_error("graph scratch not set");
+  engine->makeCurrent();
+  auto ptrOf = [&](int node) -> void* {
+    return static_cast<uint8_t*>(scratchBase) + planner.getAllocByteOffset(nodes[node].allocID);
+  };
+
+  // Weight reorder + pad + upload (core/graph.cpp:113-140), once per graph.
+  if (!weightBuffer && privateByteSize > 0)
+  {
+    std::vector<uint8_t> host(privateByteSize, 0);
+    for (const ConvRecord& r : convs)
+    {
+      const std::vector<uint16_t> w = asHalfBits(*r.weight), b = asHalfBits(*r.bias);
+      r.conv->packWeight(w.data(), r.weight->dims[0], r.I1, r.I2, host.data() + r.weightOffset);
+      r.conv->packBias(b.data(), r.bias->dims[0], host.data() + r.biasOffset);
+    }
+    weightBuffer = engine->malloc(privateByteSize);
+    checkCuda(cudaMemcpy(weightBuffer, host.data(), privateByteSize, cudaMemcpyHostToDevice), "weight upload");
+  }
+
+  for (const ConvRecord& r : convs)
+  {
+    r.conv->setSrc(ptrOf(r.src1), r.src2 >= 0 ? ptrOf(r.src2) : nullptr);
+    r.conv->setWeight(static_cast<uint8_t*>(weightBuffer) + r.weightOffset);
+    r.conv->setBias(static_cast<uint8_t*>(weightBuffer) + r.biasOffset);
+    r.conv->setDst(ptrOf(r.dst));
+    r.conv->finalize();
+  }
+  if (inputProcess) inputProcess->setDst(ptrOf(inputNode));
+  if (outputProcess) outputProcess->setSrc(ptrOf(outputSrcNode));
+  finalized = true;
+}
+
+void Graph::submit()
+{
+  if (!finalized) throw std::logic_error("graph not finalized");
+  engine->makeCurrent();
+  for (auto& op : ops) op->submit();
+}
+
+} // namespace oidnb200

@@ -1,0 +1,87 @@
+// Graph: the op list of one UNet instance on one engine, its weights and its scratch plan.
+// Interface follows core/graph.h:27-64 (addInputProcess / addConv / addConcatConv /
+// addOutputProcess / getScratchByteSize / setScratch / finalize / submit); the construction is the
+// fused B200 design:
+//   * PostOp::Pool runs in the producing conv's epilogue (the un-pooled tensor never exists);
+//   * PostOp::Upsample produces a *virtual* tensor: it is stored at the conv's own resolution and
+//     every consumer reads it through a TMA map with a stride-0 duplication axis;
+//   * ConcatConv is one kernel with two K segments reading both sources in place.
+#pragma once
+#include "arena_planner.hpp"
+#include "engine.hpp"
+#include "tza.hpp"
+#include <vector>
+
+namespace oidnb200 {
+
+class Graph
+{
+public:
+  // A value flowing between ops: stored tensor + whether consumers see it 2x nearest-upsampled.
+  struct Value
+  {
+    int id = -1;
+  };
+
+  Graph(Engine* engine, std::shared_ptr<TensorMap> constTensors);
+  ~Graph();
+
+  Value addInputProcess(const std::string& name, const TensorDesc& dstDesc,
+                        const std::shared_ptr<TransferFunction>& tf, bool hdr, bool snorm);
+  void addOutputProcess(const std::string& name, Value src, const std::shared_ptr<TransferFunction>& tf,
+                        bool hdr, bool snorm);
+  Value addConv(const std::string& name, Value src, Activation activation, PostOp postOp = PostOp::None);
+  Value addConcatConv(const std::string& name, Value src1, Value src2, Activation activation);
+
+  size_t getScratchByteSize();               // planned arena size for the intermediate tensors
+  size_t getPrivateByteSize() const { return privateByteSize; } // packed weights + biases
+  void setScratch(void* base, size_t byteSize);
+  void finalize();                           // upload weights, bind pointers, encode tensor maps
+  void submit();                             // launch every op in order on the engine's stream
+  void clear();
+
+  const std::shared_ptr<InputProcess>& getInputProcess() const { return inputProcess; }
+  const std::shared_ptr<OutputProcess>& getOutputProcess() const { return outputProcess; }
+  int getNumOps() const { return (int)ops.size(); }
+  const std::vector<std::shared_ptr<Op>>& getOps() const { return ops; }
+  const ArenaPlanner& getPlanner() const { return planner; }
+  // logical (consumer-visible) dims of a value
+  TensorDesc getLogicalDesc(Value v) const;
+
+private:
+  struct Node
+  {
+    TensorDesc stored;   // what lives in the arena
+    bool upsampled;      // consumers see 2H x 2W
+    int allocID;
+    int opID;
+  };
+  struct ConvRecord
+  {
+    std::shared_ptr<Conv> conv;
+    int src1, src2, dst;        // node ids (src2 = -1 for plain conv)
+    size_t weightOffset, biasOffset;
+    const ConstTensor *weight, *bias;
+    int I1, I2;
+  };
+
+  const ConstTensor& findConst(const std::string& name) const;
+  Value addConvImpl(const std::string& name, Value src1, Value src2, Activation activation, PostOp postOp);
+
+  Engine* engine;
+  std::shared_ptr<TensorMap> constTensors;
+  std::vector<std::shared_ptr<Op>> ops;
+  std::vector<Node> nodes;
+  std::vector<ConvRecord> convs;
+  std::shared_ptr<InputProcess> inputProcess;
+  std::shared_ptr<OutputProcess> outputProcess;
+  int inputNode = -1, outputSrcNode = -1;
+  ArenaPlanner planner;
+  bool planned = false, finalized = false;
+  size_t privateByteSize = 0;
+  void* scratchBase = nullptr;
+  size_t scratchSize = 0;
+  void* weightBuffer = nullptr;
+};
+
+} // namespace oidnb200

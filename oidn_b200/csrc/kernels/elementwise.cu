@@ -1,0 +1,682 @@
+// Bandwidth-bound passes of the denoising path: input process, output process, autoexposure,
+// image copy, and the stand-alone pool / upsample ops.
+//
+// Functional spec: devices/gpu/gpu_input_process.h:37-176, gpu_output_process.h:35-73,
+// gpu_autoexposure.h:13-164, gpu_image_copy.h:15-27, gpu_pool.h:33-52, gpu_upsample.h:33-52 and
+// their CPU twins (devices/cpu/cpu_input_process.isph:31-136, cpu_output_process.isph:29-70,
+// cpu_autoexposure.cpp:22-64). Transfer functions: core/color.h:29-165.
+//
+// These kernels move bytes: each thread owns whole pixels, tensor stores are 16-byte vectors
+// (one pixel of the 16-channel network input is two of them), packed fp32 RGB images are read as
+// float4 triples (4 pixels = 48 B), and the autoexposure is a single pass with warp-shuffle
+// reductions and a last-block-done final reduction instead of three launches.
+#include "common.h"
+#include "../../../include/oidn_b200_kernels.h"
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+#include <string>
+
+namespace oidnb200 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Image accessor (core/image_accessor.h:16-94): C==1 -> (x,x,x), C==2 -> (x,y,y)
+// ------------------------------------------------------------------------------------------------
+struct Img
+{
+  uint8_t* ptr;
+  int C;
+  int is_half;
+  int W, H;
+  size_t ps, rs;
+};
+
+bool make_img(const oidnb200_image* im, Img& o)
+{
+  o = Img{nullptr, 0, 0, 0, 0, 0, 0};
+  if (!im || !im->ptr) return true;
+  switch (im->format)
+  {
+  case OIDNB200_FORMAT_FLOAT: case OIDNB200_FORMAT_FLOAT2: case OIDNB200_FORMAT_FLOAT3:
+    o.C = im->format - OIDNB200_FORMAT_FLOAT + 1; o.is_half = 0; break;
+  case OIDNB200_FORMAT_HALF: case OIDNB200_FORMAT_HALF2: case OIDNB200_FORMAT_HALF3:
+    o.C = im->format - OIDNB200_FORMAT_HALF + 1; o.is_half = 1; break;
+  default:
+    return false;
+  }
+  o.ptr = static_cast<uint8_t*>(im->ptr);
+  o.W = im->W; o.H = im->H; o.ps = im->pixel_stride; o.rs = im->row_stride;
+  return true;
+}
+
+__device__ __forceinline__ float3 img_get3(const Img& im, int h, int w)
+{
+  const uint8_t* px = im.ptr + (size_t)h * im.rs + (size_t)w * im.ps;
+  float x, y, z;
+  if (im.is_half)
+  {
+    const __half* p = reinterpret_cast<const __half*>(px);
+    x = __half2float(p[0]);
+    y = im.C >= 2 ? __half2float(p[1]) : x;
+    z = im.C == 3 ? __half2float(p[2]) : y;
+  }
+  else
+  {
+    const float* p = reinterpret_cast<const float*>(px);
+    x = p[0];
+    y = im.C >= 2 ? p[1] : x;
+    z = im.C == 3 ? p[2] : y;
+  }
+  return make_float3(x, y, z);
+}
+
+__device__ __forceinline__ void img_set3(const Img& im, int h, int w, float3 v)
+{
+  uint8_t* px = im.ptr + (size_t)h * im.rs + (size_t)w * im.ps;
+  if (im.is_half)
+  {
+    __half* p = reinterpret_cast<__half*>(px);
+    p[0] = __float2half_rn(v.x);
+    if (im.C >= 2) p[1] = __float2half_rn(v.y);
+    if (im.C == 3) p[2] = __float2half_rn(v.z);
+  }
+  else
+  {
+    float* p = reinterpret_cast<float*>(px);
+    p[0] = v.x;
+    if (im.C >= 2) p[1] = v.y;
+    if (im.C == 3) p[2] = v.z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transfer function (core/color.h:29-165)
+// ------------------------------------------------------------------------------------------------
+struct Transfer
+{
+  int type;
+  float norm, rcp_norm;
+  float input_scale;
+  const float* input_scale_ptr;
+};
+
+constexpr float kSrgbA = 12.92f, kSrgbB = 1.055f, kSrgbC = 1.f / 2.4f, kSrgbD = -0.055f;
+constexpr float kSrgbY0 = 0.0031308f, kSrgbX0 = 0.04045f;
+constexpr float kPuA = 1.41283765e+03f, kPuB = 1.64593172e+00f, kPuC = 4.31384981e-01f;
+constexpr float kPuD = -2.94139609e-03f, kPuE = 1.92653254e-01f, kPuF = 6.26026094e-03f;
+constexpr float kPuG = 9.98620152e-01f, kPuY0 = 1.57945760e-06f, kPuY1 = 3.22087631e-02f;
+constexpr float kPuX0 = 2.23151711e-03f, kPuX1 = 3.70974749e-01f;
+
+__host__ __device__ inline float tf_raw_forward(int type, float y)
+{
+  switch (type)
+  {
+  case OIDNB200_TF_SRGB:
+    return y <= kSrgbY0 ? kSrgbA * y : kSrgbB * powf(y, kSrgbC) + kSrgbD;
+  case OIDNB200_TF_PU:
+    if (y <= kPuY0) return kPuA * y;
+    if (y <= kPuY1) return kPuB * powf(y, kPuC) + kPuD;
+    return kPuE * logf(y + kPuF) + kPuG;
+  case OIDNB200_TF_LOG:
+    return logf(y + 1.f);
+  default:
+    return y;
+  }
+}
+
+__device__ __forceinline__ float tf_forward(const Transfer& t, float y)
+{
+  const float x = tf_raw_forward(t.type, y);
+  return (t.type == OIDNB200_TF_PU || t.type == OIDNB200_TF_LOG) ? x * t.norm : x;
+}
+
+__device__ __forceinline__ float tf_inverse(const Transfer& t, float x)
+{
+  switch (t.type)
+  {
+  case OIDNB200_TF_SRGB:
+    return x <= kSrgbX0 ? x / kSrgbA : powf((x - kSrgbD) / kSrgbB, 1.f / kSrgbC);
+  case OIDNB200_TF_PU:
+  {
+    const float u = x * t.rcp_norm;
+    if (u <= kPuX0) return u / kPuA;
+    if (u <= kPuX1) return powf((u - kPuD) / kPuB, 1.f / kPuC);
+    return expf((u - kPuG) / kPuE) - kPuF;
+  }
+  case OIDNB200_TF_LOG:
+    return expf(x * t.rcp_norm) - 1.f;
+  default:
+    return x;
+  }
+}
+
+bool make_transfer(const oidnb200_transfer* tf, Transfer& t)
+{
+  if (!tf || tf->type < OIDNB200_TF_LINEAR || tf->type > OIDNB200_TF_LOG) return false;
+  t.type = tf->type;
+  // core/color.cpp:9-16: normScale = 1/forward(yMax), evaluated on the host in fp32
+  const float xmax = tf_raw_forward(tf->type, 65504.f);
+  t.norm = (float)(1. / xmax);
+  t.rcp_norm = xmax;
+  t.input_scale = tf->input_scale;
+  t.input_scale_ptr = tf->input_scale_ptr;
+  return true;
+}
+
+__device__ __forceinline__ float nan_to_zero(float x) { return isnan(x) ? 0.f : x; }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b)
+{
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input process
+// ------------------------------------------------------------------------------------------------
+struct InputParams
+{
+  Img input, albedo, normal;
+  oidnb200_tile tile;
+  Transfer tf;
+  int hdr, snorm;
+  __half* dst;
+  int TH, TW, C; // C = 16
+};
+
+__device__ __forceinline__ void input_pixel(const InputParams& p, float scale, float3 c, float3 a, float3 n,
+                                            bool has_a, bool has_n, uint4& lo, uint4& hi)
+{
+  const float cmin = p.snorm ? -1.f : 0.f, cmax = p.hdr ? FLT_MAX : 1.f;
+  float v[3] = {c.x, c.y, c.z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    float x = clampf(nan_to_zero(v[k] * scale), cmin, cmax);
+    if (p.snorm) x = x * 0.5f + 0.5f;
+    v[k] = tf_forward(p.tf, x);
+  }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+  if (has_a)
+  {
+    a0 = clampf(nan_to_zero(a.x), 0.f, 1.f); a1 = clampf(nan_to_zero(a.y), 0.f, 1.f); a2 = clampf(nan_to_zero(a.z), 0.f, 1.f);
+  }
+  if (has_n)
+  {
+    n0 = clampf(nan_to_zero(n.x), -1.f, 1.f) * 0.5f + 0.5f;
+    n1 = clampf(nan_to_zero(n.y), -1.f, 1.f) * 0.5f + 0.5f;
+    n2 = clampf(nan_to_zero(n.z), -1.f, 1.f) * 0.5f + 0.5f;
+  }
+  lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], a0), pack2(a1, a2), pack2(n0, n1));
+  hi = make_uint4(pack2(n2, 0.f), 0u, 0u, 0u);
+}
+
+// Generic path: one thread per tile-buffer pixel, any format / strides.
+__global__ void __launch_bounds__(256) input_process_kernel(const InputParams p)
+{
+  const int wd = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hd = blockIdx.y;
+  if (wd >= p.TW) return;
+  const int h = hd - p.tile.hDstBegin, w = wd - p.tile.wDstBegin;
+  uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+  if (h >= 0 && h < p.tile.H && w >= 0 && w < p.tile.W)
+  {
+    const int hs = h + p.tile.hSrcBegin, ws = w + p.tile.wSrcBegin;
+    const float scale = p.tf.input_scale_ptr ? *p.tf.input_scale_ptr : p.tf.input_scale;
+    const bool has_a = p.albedo.ptr != nullptr, has_n = has_a && p.normal.ptr != nullptr;
+    const float3 c = img_get3(p.input, hs, ws);
+    const float3 a = has_a ? img_get3(p.albedo, hs, ws) : make_float3(0, 0, 0);
+    const float3 n = has_n ? img_get3(p.normal, hs, ws) : make_float3(0, 0, 0);
+    input_pixel(p, scale, c, a, n, has_a, has_n, lo, hi);
+  }
+  uint4* d = reinterpret_cast<uint4*>(p.dst + ((size_t)hd * p.TW + wd) * 16);
+  d[0] = lo;
+  d[1] = hi;
+}
+
+// Fast path: packed fp32 RGB images (pixel stride 12 B, 16-B aligned rows), tile origins and
+// widths multiples of 4 pixels. One thread owns 4 consecutive pixels: three float4 loads per
+// image (48 B) and eight 16-B stores.
+__device__ __forceinline__ void load4px(const Img& im, int hs, int ws, float3 (&o)[4])
+{
+  const float4* q = reinterpret_cast<const float4*>(im.ptr + (size_t)hs * im.rs + (size_t)ws * 12);
+  const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+  o[0] = make_float3(q0.x, q0.y, q0.z);
+  o[1] = make_float3(q0.w, q1.x, q1.y);
+  o[2] = make_float3(q1.z, q1.w, q2.x);
+  o[3] = make_float3(q2.y, q2.z, q2.w);
+}
+
+__global__ void __launch_bounds__(256) input_process_vec4_kernel(const InputParams p)
+{
+  const int wd = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int hd = blockIdx.y;
+  if (wd >= p.TW) return;
+  const int h = hd - p.tile.hDstBegin, w = wd - p.tile.wDstBegin;
+  uint4* d = reinterpret_cast<uint4*>(p.dst + ((size_t)hd * p.TW + wd) * 16);
+  if (h >= 0 && h < p.tile.H && w >= 0 && w < p.tile.W) // all four pixels inside (W, wDstBegin multiples of 4)
+  {
+    const int hs = h + p.tile.hSrcBegin, ws = w + p.tile.wSrcBegin;
+    const float scale = p.tf.input_scale_ptr ? *p.tf.input_scale_ptr : p.tf.input_scale;
+    const bool has_a = p.albedo.ptr != nullptr, has_n = has_a && p.normal.ptr != nullptr;
+    float3 c[4], a[4], n[4];
+    load4px(p.input, hs, ws, c);
+    if (has_a) load4px(p.albedo, hs, ws, a);
+    if (has_n) load4px(p.normal, hs, ws, n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      uint4 lo, hi;
+      input_pixel(p, scale, c[i], a[i], n[i], has_a, has_n, lo, hi);
+      d[2 * i] = lo;
+      d[2 * i + 1] = hi;
+    }
+  }
+  else
+  {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = z;
+  }
+}
+
+bool packed_rgb32(const Img& im)
+{
+  return !im.ptr || (!im.is_half && im.C == 3 && im.ps == 12 && im.rs % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(im.ptr) % 16 == 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output process
+// ------------------------------------------------------------------------------------------------
+struct OutputParams
+{
+  const __half* src;
+  int TH, TW, C;
+  oidnb200_tile tile;
+  Transfer tf;
+  int hdr, snorm;
+  Img dst;
+};
+
+__device__ __forceinline__ float3 output_pixel(const OutputParams& p, float oscale, float x, float y, float z)
+{
+  float v[3] = {x, y, z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    v[k] = tf_inverse(p.tf, clampf(nan_to_zero(v[k]), 0.f, FLT_MAX));
+  if (p.dst.C == 1)
+  {
+    const float m = (v[0] + v[1] + v[2]) * (1.f / 3.f);
+    v[0] = v[1] = v[2] = m;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    if (p.snorm) v[k] = fmaxf(v[k] * 2.f - 1.f, -1.f);
+    if (!p.hdr) v[k] = fminf(v[k], 1.f);
+    v[k] *= oscale;
+  }
+  return make_float3(v[0], v[1], v[2]);
+}
+
+__device__ __forceinline__ float output_scale(const Transfer& tf)
+{
+  const float s = tf.input_scale_ptr ? *tf.input_scale_ptr : tf.input_scale;
+  return s != 0.f ? 1.f / s : 0.f; // core/color.h:95-123
+}
+
+__global__ void __launch_bounds__(256) output_process_kernel(const OutputParams p)
+{
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y;
+  if (w >= p.tile.W) return;
+  const __half* s = p.src + ((size_t)(h + p.tile.hSrcBegin) * p.TW + (w + p.tile.wSrcBegin)) * p.C;
+  const uint2 raw = *reinterpret_cast<const uint2*>(s); // channels 0..3
+  const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
+  const float3 v = output_pixel(p, output_scale(p.tf), __low2float(h01), __high2float(h01), __low2float(h23));
+  img_set3(p.dst, h + p.tile.hDstBegin, w + p.tile.wDstBegin, v);
+}
+
+// Packed fp32 RGB destination, tile origin/width multiples of 4 pixels: 4 pixels per thread,
+// three float4 stores.
+__global__ void __launch_bounds__(256) output_process_vec4_kernel(const OutputParams p)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int h = blockIdx.y;
+  if (w >= p.tile.W) return;
+  const float oscale = output_scale(p.tf);
+  const __half* s = p.src + ((size_t)(h + p.tile.hSrcBegin) * p.TW + (w + p.tile.wSrcBegin)) * p.C;
+  float3 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+  {
+    const uint2 raw = *reinterpret_cast<const uint2*>(s + (size_t)i * p.C);
+    const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
+    v[i] = output_pixel(p, oscale, __low2float(h01), __high2float(h01), __low2float(h23));
+  }
+  float4* d = reinterpret_cast<float4*>(p.dst.ptr + (size_t)(h + p.tile.hDstBegin) * p.dst.rs +
+                                        (size_t)(w + p.tile.wDstBegin) * 12);
+  d[0] = make_float4(v[0].x, v[0].y, v[0].z, v[1].x);
+  d[1] = make_float4(v[1].y, v[1].z, v[2].x, v[2].y);
+  d[2] = make_float4(v[2].z, v[3].x, v[3].y, v[3].z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Autoexposure: one launch. Each warp reduces whole bins (<=16x16 px: lane = column + 16*(row&1),
+// 8 row pairs), keeps log2(mean luminance) of its bins in registers; block partials go to scratch;
+// the last block to finish folds the partials in a fixed order (deterministic) and writes the scale.
+// ------------------------------------------------------------------------------------------------
+struct AutoexposureParams
+{
+  Img src;
+  int nbh, nbw;
+  float* block_sums;   // [gridDim.x]
+  int* block_counts;   // [gridDim.x]
+  unsigned int* ticket;
+  float* dst;
+};
+
+constexpr int kAeThreads = 256;
+
+__global__ void __launch_bounds__(kAeThreads) autoexposure_kernel(const AutoexposureParams p)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = kAeThreads / 32;
+  const int nbins = p.nbh * p.nbw;
+  const int col = lane & 15, rpar = lane >> 4;
+  float wsum = 0.f;
+  int wcount = 0;
+  for (int bin = blockIdx.x * nwarps + warp; bin < nbins; bin += gridDim.x * nwarps)
+  {
+    const int bi = bin / p.nbw, bj = bin - bi * p.nbw;
+    const int h0 = (int)((long long)bi * p.src.H / p.nbh), h1 = (int)((long long)(bi + 1) * p.src.H / p.nbh);
+    const int w0 = (int)((long long)bj * p.src.W / p.nbw), w1 = (int)((long long)(bj + 1) * p.src.W / p.nbw);
+    float L = 0.f;
+    const int w = w0 + col;
+    if (w < w1)
+      for (int h = h0 + rpar; h < h1; h += 2)
+      {
+        const float3 c = img_get3(p.src, h, w);
+        const float r = clampf(nan_to_zero(c.x), 0.f, FLT_MAX), g = clampf(nan_to_zero(c.y), 0.f, FLT_MAX),
+                    b = clampf(nan_to_zero(c.z), 0.f, FLT_MAX);
+        L += 0.212671f * r + 0.715160f * g + 0.072169f * b; // core/color.h:169-172
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+    L /= (float)((h1 - h0) * (w1 - w0));
+    if (L > 1e-8f) { wsum += log2f(L); wcount++; } // identical on all lanes
+  }
+  __shared__ float ssum[kAeThreads / 32];
+  __shared__ int scnt[kAeThreads / 32];
+  __shared__ bool last;
+  if (lane == 0) { ssum[warp] = wsum; scnt[warp] = wcount; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    float s = 0.f; int c = 0;
+    for (int i = 0; i < nwarps; ++i) { s += ssum[i]; c += scnt[i]; }
+    p.block_sums[blockIdx.x] = s;
+    p.block_counts[blockIdx.x] = c;
+    __threadfence();
+    const unsigned int t = atomicAdd(p.ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && warp == 0)
+  {
+    __threadfence();
+    double s = 0.; long long c = 0;
+    for (int i = lane; i < (int)gridDim.x; i += 32)
+    {
+      s += (double)reinterpret_cast<volatile float*>(p.block_sums)[i];
+      c += reinterpret_cast<volatile int*>(p.block_counts)[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0)
+    {
+      *p.dst = c > 0 ? 0.18f / exp2f((float)(s / (double)c)) : 1.f;
+      *p.ticket = 0; // re-arm for the next frame
+    }
+  }
+}
+
+int autoexposure_grid(int nbins)
+{
+  const int per_block = kAeThreads / 32;
+  int g = (nbins + per_block - 1) / per_block;
+  const int cap = 148 * 8;
+  return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Image copy, pool, upsample
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) image_copy_kernel(const Img src, const Img dst, int px_bytes)
+{
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y;
+  if (w >= dst.W) return;
+  const uint8_t* s = src.ptr + (size_t)h * src.rs + (size_t)w * src.ps;
+  uint8_t* d = dst.ptr + (size_t)h * dst.rs + (size_t)w * dst.ps;
+  if (src.is_half)
+    for (int i = 0; i < px_bytes; i += 2) *reinterpret_cast<uint16_t*>(d + i) = *reinterpret_cast<const uint16_t*>(s + i);
+  else
+    for (int i = 0; i < px_bytes; i += 4) *reinterpret_cast<uint32_t*>(d + i) = *reinterpret_cast<const uint32_t*>(s + i);
+}
+
+__device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// one thread per 8 channels (16 B) of one output pixel
+__global__ void __launch_bounds__(256) pool_kernel(const uint4* __restrict__ src, int H, int W, int C8, uint4* __restrict__ dst)
+{
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Ho = H / 2, Wo = W / 2;
+  if (idx >= (long)Ho * Wo * C8) return;
+  const int c = (int)(idx % C8);
+  const int x = (int)((idx / C8) % Wo);
+  const int y = (int)(idx / ((long)C8 * Wo));
+  const uint4 a = src[((size_t)(2 * y) * W + 2 * x) * C8 + c], b = src[((size_t)(2 * y) * W + 2 * x + 1) * C8 + c];
+  const uint4 d = src[((size_t)(2 * y + 1) * W + 2 * x) * C8 + c], e = src[((size_t)(2 * y + 1) * W + 2 * x + 1) * C8 + c];
+  uint4 r;
+  r.x = hmax2u(hmax2u(a.x, b.x), hmax2u(d.x, e.x));
+  r.y = hmax2u(hmax2u(a.y, b.y), hmax2u(d.y, e.y));
+  r.z = hmax2u(hmax2u(a.z, b.z), hmax2u(d.z, e.z));
+  r.w = hmax2u(hmax2u(a.w, b.w), hmax2u(d.w, e.w));
+  dst[idx] = r;
+}
+
+__global__ void __launch_bounds__(256) upsample_kernel(const uint4* __restrict__ src, int H, int W, int C8, uint4* __restrict__ dst)
+{
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Ho = H * 2, Wo = W * 2;
+  if (idx >= (long)Ho * Wo * C8) return;
+  const int c = (int)(idx % C8);
+  const int x = (int)((idx / C8) % Wo);
+  const int y = (int)(idx / ((long)C8 * Wo));
+  dst[idx] = src[((size_t)(y >> 1) * W + (x >> 1)) * C8 + c];
+}
+
+int check_launch(const char* what)
+{
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+  {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+} // namespace
+} // namespace oidnb200
+
+using namespace oidnb200;
+
+extern "C" {
+
+int oidnb200_input_process_launch(const oidnb200_image* color, const oidnb200_image* albedo,
+                                  const oidnb200_image* normal, const oidnb200_tile* tile,
+                                  const oidnb200_transfer* tf, int hdr, int snorm, void* dst, int TH, int TW,
+                                  int C, oidnb200_stream stream)
+{
+  InputParams p;
+  if (!make_img(color, p.input) || !make_img(albedo, p.albedo) || !make_img(normal, p.normal) || !p.input.ptr)
+  {
+    set_error("input_process: missing main input image or unsupported image format");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (!tile || !dst || C != 16 || TH <= 0 || TW <= 0 || !make_transfer(tf, p.tf))
+  {
+    set_error("input_process: bad arguments (the network input tensor has 16 channels)");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (tile->H < 0 || tile->W < 0 || tile->hDstBegin < 0 || tile->wDstBegin < 0 ||
+      tile->hDstBegin + tile->H > TH || tile->wDstBegin + tile->W > TW || tile->hSrcBegin < 0 ||
+      tile->wSrcBegin < 0 || tile->hSrcBegin + tile->H > p.input.H || tile->wSrcBegin + tile->W > p.input.W)
+  {
+    set_error("input_process: tile outside the image or the tile buffer");
+    return OIDNB200_ERR_INVALID;
+  }
+  p.tile = *tile; p.hdr = hdr; p.snorm = snorm;
+  p.dst = static_cast<__half*>(dst); p.TH = TH; p.TW = TW; p.C = C;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = packed_rgb32(p.input) && packed_rgb32(p.albedo) && packed_rgb32(p.normal) && TW % 4 == 0 &&
+                   tile->W % 4 == 0 && tile->wDstBegin % 4 == 0 && tile->wSrcBegin % 4 == 0;
+  if (vec)
+  {
+    const int threads = 128;
+    dim3 grid((TW / 4 + threads - 1) / threads, TH);
+    input_process_vec4_kernel<<<grid, threads, 0, st>>>(p);
+  }
+  else
+  {
+    const int threads = 256;
+    dim3 grid((TW + threads - 1) / threads, TH);
+    input_process_kernel<<<grid, threads, 0, st>>>(p);
+  }
+  return check_launch("input_process");
+}
+
+int oidnb200_output_process_launch(const void* src, int TH, int TW, int C, const oidnb200_tile* tile,
+                                   const oidnb200_transfer* tf, int hdr, int snorm, const oidnb200_image* dst,
+                                   oidnb200_stream stream)
+{
+  OutputParams p;
+  if (!src || !tile || !make_img(dst, p.dst) || !p.dst.ptr || !make_transfer(tf, p.tf) || C < 4 || C % 4)
+  {
+    set_error("output_process: bad arguments");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (tile->H < 0 || tile->W < 0 || tile->hSrcBegin < 0 || tile->wSrcBegin < 0 || tile->hSrcBegin + tile->H > TH ||
+      tile->wSrcBegin + tile->W > TW || tile->hDstBegin < 0 || tile->wDstBegin < 0 ||
+      tile->hDstBegin + tile->H > p.dst.H || tile->wDstBegin + tile->W > p.dst.W)
+  {
+    set_error("output_process: tile outside the tensor or the image");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (tile->H == 0 || tile->W == 0) return 0;
+  p.src = static_cast<const __half*>(src); p.TH = TH; p.TW = TW; p.C = C;
+  p.tile = *tile; p.hdr = hdr; p.snorm = snorm;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = packed_rgb32(p.dst) && tile->W % 4 == 0 && tile->wDstBegin % 4 == 0;
+  if (vec)
+  {
+    const int threads = 128;
+    dim3 grid((tile->W / 4 + threads - 1) / threads, tile->H);
+    output_process_vec4_kernel<<<grid, threads, 0, st>>>(p);
+  }
+  else
+  {
+    const int threads = 256;
+    dim3 grid((tile->W + threads - 1) / threads, tile->H);
+    output_process_kernel<<<grid, threads, 0, st>>>(p);
+  }
+  return check_launch("output_process");
+}
+
+size_t oidnb200_autoexposure_scratch_bytes(int H, int W)
+{
+  const int nbins = ((H + 15) / 16) * ((W + 15) / 16);
+  const int g = autoexposure_grid(nbins);
+  return 256 + (size_t)g * 8; // ticket (own 256-B line) + per-block sum and count
+}
+
+int oidnb200_autoexposure_launch(const oidnb200_image* src, void* scratch, float* dst, oidnb200_stream stream)
+{
+  AutoexposureParams p;
+  if (!make_img(src, p.src) || !p.src.ptr || !scratch || !dst || p.src.H <= 0 || p.src.W <= 0)
+  {
+    set_error("autoexposure: bad arguments");
+    return OIDNB200_ERR_INVALID;
+  }
+  p.nbh = (p.src.H + 15) / 16; p.nbw = (p.src.W + 15) / 16;
+  const int g = autoexposure_grid(p.nbh * p.nbw);
+  uint8_t* s = static_cast<uint8_t*>(scratch);
+  p.ticket = reinterpret_cast<unsigned int*>(s);
+  p.block_sums = reinterpret_cast<float*>(s + 256);
+  p.block_counts = reinterpret_cast<int*>(s + 256 + (size_t)g * 4);
+  p.dst = dst;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // The ticket must start at zero; the kernel re-arms it, the memset covers fresh scratch.
+  cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st);
+  autoexposure_kernel<<<g, kAeThreads, 0, st>>>(p);
+  return check_launch("autoexposure");
+}
+
+int oidnb200_image_copy_launch(const oidnb200_image* src, const oidnb200_image* dst, oidnb200_stream stream)
+{
+  Img s, d;
+  if (!make_img(src, s) || !make_img(dst, d) || !s.ptr || !d.ptr || s.W != d.W || s.H != d.H ||
+      src->format != dst->format)
+  {
+    set_error("image_copy: images must be set and have the same size and format");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (d.W == 0 || d.H == 0) return 0;
+  const int threads = 256;
+  dim3 grid((d.W + threads - 1) / threads, d.H);
+  image_copy_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(s, d, s.C * (s.is_half ? 2 : 4));
+  return check_launch("image_copy");
+}
+
+int oidnb200_pool_launch(const void* src, int H, int W, int C, void* dst, oidnb200_stream stream)
+{
+  if (!src || !dst || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || C % 8)
+  {
+    set_error("pool: needs even H, W and C a multiple of 8");
+    return OIDNB200_ERR_INVALID;
+  }
+  const long n = (long)(H / 2) * (W / 2) * (C / 8);
+  pool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    static_cast<const uint4*>(src), H, W, C / 8, static_cast<uint4*>(dst));
+  return check_launch("pool");
+}
+
+int oidnb200_upsample_launch(const void* src, int H, int W, int C, void* dst, oidnb200_stream stream)
+{
+  if (!src || !dst || H <= 0 || W <= 0 || C <= 0 || C % 8)
+  {
+    set_error("upsample: needs C a multiple of 8");
+    return OIDNB200_ERR_INVALID;
+  }
+  const long n = (long)(H * 2) * (W * 2) * (C / 8);
+  upsample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    static_cast<const uint4*>(src), H, W, C / 8, static_cast<uint4*>(dst));
+  return check_launch("upsample");
+}
+
+} // extern "C"

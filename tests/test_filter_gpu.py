@@ -1,0 +1,308 @@
+"""-m gpu: the RT / RTLightmap filters through the filter-level C ABI against the CPU oracle and the
+committed golden vectors (reference PyTorch), plus the reference's own behavioural tests
+(apps/oidnTest.cpp): tiled == untiled bit-exactly, in-place, sanitisation, formats, errors.
+
+Tolerance (BASELINE.json north_star): max|out - ref| <= 1e-2 * max|ref| and PSNR >= 50 dB against
+the fp32 CPU result."""
+import numpy as np
+import pytest
+
+from oidn_b200 import api, capi, synth, weights
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from gpu_util import metrics  # noqa: E402
+from test_oracle_golden import CASES, case_inputs  # noqa: E402
+
+MAX_ERR, MIN_PSNR = 1e-2, 50.0
+
+
+@pytest.fixture(scope="module")
+def device():
+  d = api.Device((0,)).commit()
+  yield d
+  d.release()
+
+
+def run_filter(device, tza, color=None, albedo=None, normal=None, filt="RT", out_dtype=None, out_channels=None, **params):
+  """Runs the CUDA filter on numpy HxWxC inputs; returns (numpy output, filter info)."""
+  f = device.new_filter(filt)
+  keep = []
+  main = color if color is not None else (albedo if albedo is not None else normal)
+  for name, img in (("color", color), ("albedo", albedo), ("normal", normal)):
+    if img is not None:
+      t = torch.from_numpy(np.ascontiguousarray(img)).cuda(); keep.append(t)
+      f.set_image(name, t)
+  H, W = main.shape[:2]
+  Cc = out_channels or (main.shape[2] if main.ndim == 3 else 1)
+  out = torch.full((H, W, Cc), -123.0, dtype=getattr(torch, out_dtype or main.dtype.name), device="cuda")
+  f.set_image("output", out)
+  max_tile = params.pop("maxTilePixels", None)
+  if max_tile:
+    device.set("maxTilePixels", max_tile)
+  for k, v in params.items():
+    f.set(k, v)
+  f.set_data("weights", tza)
+  try:
+    f.commit()
+    f.execute()
+    info = f.info()
+  finally:
+    if max_tile:
+      device.set("maxTilePixels", 3840 * 2176)
+  res = out.cpu().numpy()
+  f.release()
+  return res, info
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_matches_reference_golden_and_oracle(case, golden, oracle, device):
+  name, kind, ic, filt, mode, W, H = case
+  tza, color, albedo, normal = case_inputs(kind, ic, mode, W, H)
+  params = {}
+  if filt == "RT":
+    params = dict(hdr=(mode == "hdr"), srgb=(mode == "srgb"))
+  elif mode == "dir":
+    params = dict(directional=True)
+  got, info = run_filter(device, tza, color, albedo, normal, filt, **params)
+  assert info["largeModel"] == int(kind == "large")
+  ref_torch = golden[name + "/output"]               # reference PyTorch fp32
+  ref_oracle = np.zeros((H, W, 3), np.float32)       # C restatement of the reference CPU device
+  oracle.filter_execute(tza, color=color, albedo=albedo, normal=normal, output=ref_oracle, filter=filt,
+                        hdr=(mode == "hdr"), srgb=(mode == "srgb"), directional=(mode == "dir"))
+  for ref in (ref_torch, ref_oracle):
+    if mode == "dir":   # signed output: measure on the [0,1] mapped range like the other cases
+      e, p = metrics(got * 0.5 + 0.5, ref * 0.5 + 0.5)
+    else:
+      e, p = metrics(got, ref)
+    assert e <= MAX_ERR and p >= MIN_PSNR, (name, e, p)
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (2, 2), (17, 5), (257, 89), (640, 368)])
+def test_sizes_hdr_alb_nrm(W, H, oracle, device):
+  tza = weights.model_tza("base", 9, seed=0)
+  imgs = synth.benchmark_images(W, H, hdr=True, seed=2)
+  got, _ = run_filter(device, tza, imgs["color"], imgs["albedo"], imgs["normal"], hdr=True)
+  ref = np.zeros((H, W, 3), np.float32)
+  oracle.filter_execute(tza, color=imgs["color"], albedo=imgs["albedo"], normal=imgs["normal"], output=ref, hdr=True)
+  e, p = metrics(got, ref)
+  assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+
+
+def test_zero_size_image_is_noop(device):
+  """core/unet_filter.cpp:150-151: a 0x0 image commits and executes as a no-op."""
+  f = device.new_filter("RT")
+  keep = torch.zeros(16, device="cuda")
+  f.set_image("color", keep.data_ptr(), capi.FORMAT_FLOAT3, 0, 0)
+  f.set_image("output", keep.data_ptr(), capi.FORMAT_FLOAT3, 0, 0)
+  f.set_data("weights", weights.model_tza("base", 3, seed=0))
+  f.commit(); f.execute()
+  f.release()
+
+
+def test_tiled_equals_untiled_bit_exact_and_inplace(device, oracle):
+  """apps/oidnTest.cpp:717-775 ("inplace filter"): forced multi-tile in-place == normal run."""
+  W, H = 1500, 900
+  tza = weights.model_tza("base", 9, seed=0)
+  imgs = synth.benchmark_images(W, H, hdr=True, seed=4)
+  whole, i1 = run_filter(device, tza, imgs["color"], imgs["albedo"], imgs["normal"], hdr=True)
+  assert i1["tileCountH"] * i1["tileCountW"] == 1
+  tiled, i2 = run_filter(device, tza, imgs["color"], imgs["albedo"], imgs["normal"], hdr=True, maxMemoryMB=0)
+  assert i2["tileCountH"] * i2["tileCountW"] > 1
+  np.testing.assert_array_equal(whole.view(np.uint32), tiled.view(np.uint32))
+
+  # in-place (output aliases color) + forced tiling goes through the temporary image + ImageCopy
+  f = device.new_filter("RT")
+  c = torch.from_numpy(imgs["color"]).cuda(); a = torch.from_numpy(imgs["albedo"]).cuda(); n = torch.from_numpy(imgs["normal"]).cuda()
+  f.set_image("color", c); f.set_image("albedo", a); f.set_image("normal", n); f.set_image("output", c)
+  f.set("hdr", True); f.set("maxMemoryMB", 0); f.set_data("weights", tza)
+  f.commit(); f.execute()
+  np.testing.assert_array_equal(c.cpu().numpy().view(np.uint32), whole.view(np.uint32))
+  f.release()
+
+
+def test_large_model_tiles(device, oracle):
+  W, H = 1200, 1000
+  tza = weights.model_tza("large", 9, seed=0)
+  imgs = synth.benchmark_images(W, H, hdr=True, seed=5)
+  whole, i1 = run_filter(device, tza, imgs["color"], imgs["albedo"], imgs["normal"], hdr=True, cleanAux=True)
+  tiled, i2 = run_filter(device, tza, imgs["color"], imgs["albedo"], imgs["normal"], hdr=True, cleanAux=True, maxMemoryMB=0)
+  assert i1["largeModel"] == 1 and i2["tileOverlap"] == 112 and i2["tileCountH"] * i2["tileCountW"] > 1
+  np.testing.assert_array_equal(whole.view(np.uint32), tiled.view(np.uint32))
+
+
+def test_image_sanitization(device):
+  """apps/oidnTest.cpp:990-1034: NaN/Inf/negative inputs give finite outputs in range."""
+  W, H = 200, 120
+  bad = [np.nan, np.inf, -np.inf, -100.0, 1e30]
+  for hdr, kind, ic in ((True, "base", 9), (False, "base", 9)):
+    tza = weights.model_tza(kind, ic, seed=0)
+    for v in bad:
+      color = np.full((H, W, 3), v, np.float32); alb = np.full((H, W, 3), v, np.float32); nrm = np.full((H, W, 3), v, np.float32)
+      got, _ = run_filter(device, tza, color, alb, nrm, hdr=hdr)
+      assert np.isfinite(got).all() and got.min() >= 0.0
+      if not hdr:
+        assert got.max() <= 1.0
+
+
+@pytest.mark.parametrize("in_dtype,out_dtype", [("float16", "float16"), ("float32", "float16"), ("float16", "float32")])
+def test_half_images(in_dtype, out_dtype, device, oracle):
+  W, H = 300, 200
+  tza = weights.model_tza("base", 9, seed=0)
+  imgs = {k: v.astype(in_dtype) for k, v in synth.benchmark_images(W, H, hdr=True, seed=6).items()}
+  got, _ = run_filter(device, tza, imgs["color"], imgs["albedo"], imgs["normal"], hdr=True, out_dtype=out_dtype)
+  ref = np.zeros((H, W, 3), out_dtype)
+  oracle.filter_execute(tza, color=imgs["color"], albedo=imgs["albedo"], normal=imgs["normal"], output=ref, hdr=True)
+  e, p = metrics(got.astype(np.float32), ref.astype(np.float32))
+  assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+
+
+def test_strided_and_single_channel_images(device, oracle):
+  """Row/pixel strides (core/image.h) and C<3 broadcast (core/image_accessor.h:30-94)."""
+  W, H = 180, 100
+  tza = weights.model_tza("base", 3, seed=0)
+  rng = np.random.default_rng(8)
+  big = rng.random((H, W + 7, 4), dtype=np.float32)
+  tb = torch.from_numpy(big).cuda()
+  view = tb[:, 3:3 + W, :3]                      # pixel stride 16 B, row stride (W+7)*16 B
+  outb = torch.zeros((H, W + 5, 4), dtype=torch.float32, device="cuda")
+  outv = outb[:, 2:2 + W, :3]
+  f = device.new_filter("RT")
+  f.set_image("color", view); f.set_image("output", outv); f.set_data("weights", tza)
+  f.commit(); f.execute()
+  got = outv.cpu().numpy()
+  color = np.ascontiguousarray(big[:, 3:3 + W, :3])
+  ref = np.zeros((H, W, 3), np.float32)
+  oracle.filter_execute(tza, color=color, output=ref)
+  e, p = metrics(got, ref)
+  assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+  assert float(outb[:, :2].abs().sum()) == 0 and float(outb[:, :, 3].abs().sum()) == 0, "wrote outside the image"
+  f.release()
+  # 1-channel in/out
+  c1 = color[:, :, :1].copy()
+  got1, _ = run_filter(device, tza, c1)
+  ref1 = np.zeros((H, W, 1), np.float32)
+  oracle.filter_execute(tza, color=c1, output=ref1)
+  e, p = metrics(got1, ref1)
+  assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+
+
+def test_input_scale_and_filter_updates(device, oracle):
+  """apps/oidnTest.cpp:779-869: pointer-only changes do not need a rebuild; param changes do."""
+  W, H = 240, 136
+  tza = weights.model_tza("base", 9, seed=0)
+  imgs = synth.benchmark_images(W, H, hdr=True, seed=3)
+  f = device.new_filter("RT")
+  t = {k: torch.from_numpy(v).cuda() for k, v in imgs.items()}
+  out = torch.zeros((H, W, 3), device="cuda")
+  for k, v in t.items():
+    f.set_image(k, v)
+  f.set_image("output", out); f.set("hdr", True); f.set("inputScale", 0.02); f.set_data("weights", tza)
+  f.commit(); f.execute()
+  ref = np.zeros((H, W, 3), np.float32)
+  oracle.filter_execute(tza, color=imgs["color"], albedo=imgs["albedo"], normal=imgs["normal"], output=ref, hdr=True, input_scale=0.02)
+  e, p = metrics(out.cpu().numpy(), ref)
+  assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+  # uncommitted change -> InvalidOperation (core/unet_filter.cpp:147-148)
+  out2 = torch.zeros((H, W, 3), device="cuda")
+  f.set_image("output", out2)
+  with pytest.raises(api.Error) as ei:
+    f.execute()
+  assert ei.value.code == capi.ERROR_INVALID_OPERATION
+  f.commit(); f.execute()
+  assert torch.equal(out, out2)
+  f.release()
+
+
+def test_error_behaviour(device):
+  tza = weights.model_tza("base", 3, seed=0)
+  f = device.new_filter("RT")
+  with pytest.raises(api.Error) as ei:
+    f.commit()                                   # no images
+  assert ei.value.code == capi.ERROR_INVALID_OPERATION
+  c = torch.zeros((32, 32, 3), device="cuda"); o = torch.zeros((32, 48, 3), device="cuda")
+  f.set_image("color", c); f.set_image("output", o); f.set_data("weights", tza)
+  with pytest.raises(api.Error) as ei:
+    f.commit()                                   # size mismatch
+  assert ei.value.code == capi.ERROR_INVALID_OPERATION
+  f.set_image("output", torch.zeros((32, 32, 3), device="cuda"))
+  f.set("hdr", True); f.set("srgb", True)
+  with pytest.raises(api.Error):
+    f.commit()
+  f.set("srgb", False)
+  f.set_data("weights", b"\x00" * 64)            # corrupted blob (apps/oidnTest.cpp:1169-1217)
+  with pytest.raises(api.Error) as ei:
+    f.commit()
+  assert ei.value.code == capi.ERROR_INVALID_OPERATION
+  with pytest.raises(api.Error) as ei:
+    f.set("quality", 3)
+  assert ei.value.code == capi.ERROR_INVALID_ARGUMENT
+  with pytest.raises(api.Error) as ei:
+    device.new_filter("Nope")
+  assert ei.value.code == capi.ERROR_INVALID_ARGUMENT
+  host = np.zeros((32, 32, 3), np.float32)        # pageable host memory is not device accessible
+  if not device.get("systemMemorySupported"):
+    with pytest.raises(api.Error) as ei:
+      f.set_image("color", host.ctypes.data, capi.FORMAT_FLOAT3, 32, 32)
+    assert ei.value.code == capi.ERROR_INVALID_ARGUMENT
+  f.release()
+
+
+def test_progress_monitor_and_cancel(device):
+  W, H = 400, 300
+  tza = weights.model_tza("base", 3, seed=0)
+  f = device.new_filter("RT")
+  c = torch.rand((H, W, 3), device="cuda"); o = torch.zeros((H, W, 3), device="cuda")
+  f.set_image("color", c); f.set_image("output", o); f.set_data("weights", tza)
+  seen = []
+  f.set_progress_monitor(lambda n: (seen.append(n), True)[1])
+  f.commit(); f.execute()
+  assert seen[0] == 0.0 and seen[-1] == 1.0 and all(b >= a for a, b in zip(seen, seen[1:]))
+  f.set_progress_monitor(lambda n: False)
+  with pytest.raises(api.Error) as ei:
+    f.execute()
+  assert ei.value.code == capi.ERROR_CANCELLED
+  f.release()
+
+
+def test_buffers_and_async(device, oracle):
+  """oidnNewBuffer / oidnWriteBuffer / oidnSetFilterImage / oidnExecuteFilterAsync + oidnSyncDevice."""
+  W, H = 128, 80
+  tza = weights.model_tza("small", 3, seed=0)
+  color = synth.benchmark_images(W, H, hdr=False, albedo=False, normal=False, seed=12)["color"]
+  nbytes = color.nbytes
+  bc = device.new_buffer(nbytes); bo = device.new_buffer(nbytes)
+  bc.write(color)
+  f = device.new_filter("RT")
+  f.set_image("color", bc, capi.FORMAT_FLOAT3, W, H); f.set_image("output", bo, capi.FORMAT_FLOAT3, W, H)
+  f.set("quality", api.QUALITY_FAST); f.set_data("weights", tza)
+  f.commit()
+  for _ in range(3):
+    f.execute_async()
+  device.sync()
+  got = np.zeros_like(color); bo.read(got)
+  ref = np.zeros_like(color)
+  oracle.filter_execute(tza, color=color, output=ref)
+  e, p = metrics(got, ref)
+  assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+  with pytest.raises(api.Error) as ei:
+    bc.write(np.zeros(nbytes + 4, np.uint8))
+  assert ei.value.code == capi.ERROR_INVALID_ARGUMENT
+  f.release(); bc.release(); bo.release()
+
+
+def test_pinned_host_images_zero_copy(device, oracle):
+  """Storage::Host images (oidn.h OIDN_STORAGE_HOST): kernels dereference pinned memory directly."""
+  W, H = 160, 96
+  tza = weights.model_tza("base", 3, seed=0)
+  color = synth.benchmark_images(W, H, hdr=False, albedo=False, normal=False, seed=13)["color"]
+  hc = torch.from_numpy(color).pin_memory(); ho = torch.zeros((H, W, 3)).pin_memory()
+  f = device.new_filter("RT")
+  f.set_image("color", hc); f.set_image("output", ho); f.set_data("weights", tza)
+  f.commit(); f.execute()
+  ref = np.zeros_like(color)
+  oracle.filter_execute(tza, color=color, output=ref)
+  e, p = metrics(ho.numpy(), ref)
+  assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+  f.release()
