@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 denoising path (BASELINE.json metric: Mpix/s and ms/frame, RT hdr+alb+nrm).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one frame through oidnb200ExecuteFilterAsync (autoexposure + input process + 16 fused
+convolutions + output process per tile). N=1: BASELINE.json configs[1] (RT filter, HDR color +
+albedo + normal, 3840x2160, quality=high -> base UNet; there is no large variant for this feature
+set). N>1 (torchrun, one rank per GPU): the 7680x4320 frame of the same filter,
+tile-sharded across the ranks; the frame lives on rank 0's GPU, every rank reads its tiles from and
+writes its output rectangles into rank 0's buffers over NVLink (CUDA IPC peer mappings), the
+autoexposure scalar is broadcast with NCCL and a 4-byte all-reduce joins the frame.
+
+Prints ONE JSON line (rank 0). `value` is device-resident throughput (inputs already in HBM), `e2e`
+is the same metric through the public API with pinned host buffers (H2D + D2H inside the timed
+region). `--impl reference` times the CPU restatement of the reference's CPU device (oracle/) on the
+host cores: the reference CPU device itself needs ISPC + oneTBB and cannot be built in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from oidn_b200 import synth, weights  # noqa: E402
+
+METRIC = "Mpix/s, RT hdr+alb+nrm (ms/frame in ms_per_step)"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    try:
+      d = json.load(open(p))
+      out = {k: float(d[k]) for k in ("hbm_gbs", "bf16_tflops") if k in d}
+      out["bf16_tflops_sustained"] = float(d.get("bf16_tflops_sustained", out.get("bf16_tflops", 0)))
+      if len(out) == 3:
+        return out, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+      pass
+  return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+  """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+  Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.rows, self.proc = [], None
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                    "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+  def window(self, t0, t1):
+    rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+    if not rows:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(int(float(r[0])) for r in rows if r[0].replace(".", "").isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
+    pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(rows[0][1])) if rows[0][1].replace(".", "").isdigit() else None,
+            "power_w": round(max(pw), 1) if pw else None, "samples": len(rows), "reasons": reasons}
+
+  def stop(self):
+    if self.proc:
+      self.proc.terminate()
+
+
+def cpu_port_throughput(tza, W, H, budget_s=20.0):
+  """Times the oracle (CPU restatement of the reference CPU device) on crops of the workload.
+  Only place besides tests/ and smoke() that executes oracle/ (as the reported CPU baseline)."""
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import oracle as orc
+  orc.lib()
+  cores = os.cpu_count() or 1
+  best = None
+  for w, h in ((480, 272), (960, 544), (1920, 1080), (W, H)):
+    if w > W or h > H:
+      break
+    imgs = synth.benchmark_images(w, h, hdr=True, seed=1)
+    out = np.zeros((h, w, 3), np.float32)
+    t0 = time.time()
+    orc.filter_execute(tza, color=imgs["color"], albedo=imgs["albedo"], normal=imgs["normal"], output=out, hdr=True)
+    dt = time.time() - t0
+    best = {"value": round(w * h / dt / 1e6, 4), "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "sample": "oracle/oidn_oracle.c (OpenMP fp32 restatement of devices/cpu) on a %dx%d frame of the same workload, %.1f s" % (w, h, dt),
+            "seconds": round(dt, 2)}
+    if dt * 4.5 > budget_s:   # the next size is 4x the pixels
+      break
+  return best
+
+
+def run_reference(args, rank):
+  if rank != 0:
+    return
+  tza = weights.model_tza("base", 9, seed=0)
+  W, H = args.width, args.height
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import oracle as orc
+  orc.lib()
+  cores = os.cpu_count() or 1
+  # one step = one bounded sample (a crop of the workload sized for ~2-4 s on this host)
+  probe = cpu_port_throughput(tza, 480, 272, budget_s=1.0)
+  px = max(480 * 272, min(W * H, int(probe["value"] * 1e6 * 3.0)))
+  w = min(W, max(480, int((px * 16 / 9) ** 0.5) // 16 * 16)); h = min(H, max(272, w * 9 // 16 // 16 * 16))
+  imgs = synth.benchmark_images(w, h, hdr=True, seed=1)
+  out = np.zeros((h, w, 3), np.float32)
+  run = lambda: orc.filter_execute(tza, color=imgs["color"], albedo=imgs["albedo"], normal=imgs["normal"], output=out, hdr=True)
+  for _ in range(args.warmup):
+    run()
+  t0 = time.time()
+  for _ in range(args.steps):
+    run()
+  dt = (time.time() - t0) / args.steps
+  val = w * h / dt / 1e6
+  sample = "oracle port (C/OpenMP restatement of the reference CPU device; the ISPC+TBB device is unbuildable here) on a %dx%d crop per step" % (w, h)
+  print(json.dumps({
+    "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+    "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+    "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+    "config": workload_config(args, args.gpus),
+    "cpu_baseline": {"value": round(val, 4), "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+    "e2e": {"value": round(val, 4), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, n):
+  W, H = frame_size(args, n)
+  return {"workload": "RT filter, HDR color+albedo+normal fp32, %dx%d, quality=high (base UNet, 16 convs), autoexposure on, "
+                      "oidnBenchmark LCG inputs, synthetic He-init TZA weights" % (W, H),
+          "width": W, "height": H, "l2": "inputs and every intermediate tensor are larger than the 126 MB L2 (no flush needed)",
+          "sharding": "single GPU" if n == 1 else "tile-sharded across %d ranks, frame resident on rank 0, NVLink peer reads/writes" % n}
+
+
+def frame_size(args, n):
+  if args.width and args.height and args.explicit_size:
+    return args.width, args.height
+  return (3840, 2160) if n == 1 else (7680, 4320)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--width", type=int, default=0)
+  ap.add_argument("--height", type=int, default=0)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-e2e", action="store_true")
+  args = ap.parse_args()
+  args.explicit_size = bool(args.width and args.height)
+  rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  args.warmup = max(args.warmup, 3 if args.impl == "ours" else 0)
+  if not args.explicit_size:
+    args.width, args.height = frame_size(args, max(world, args.gpus))
+  if args.impl == "reference":
+    args.width, args.height = frame_size(args, max(world, args.gpus)) if not args.explicit_size else (args.width, args.height)
+    run_reference(args, rank)
+    return
+
+  import torch
+  from oidn_b200 import api
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+  if world > 1:
+    from oidn_b200 import sharded
+    sharded.bench_main(args, rank, world, local_rank)
+    return
+
+  torch.cuda.set_device(local_rank)
+  W, H = args.width, args.height
+  K, Wm = args.steps, args.warmup
+  peaks, peaks_src = load_peaks()
+  tza = weights.model_tza("base", 9, seed=0)
+  imgs = synth.benchmark_images(W, H, hdr=True, seed=1)
+
+  stream = torch.cuda.Stream()
+  sampler = ClockSampler(local_rank)
+  with torch.cuda.stream(stream):
+    dev = api.Device((local_rank,), streams=[stream.cuda_stream]).commit()
+    t = {k: torch.from_numpy(v).cuda() for k, v in imgs.items()}
+    out = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    f = dev.new_filter("RT")
+    for k, v in t.items():
+      f.set_image(k, v)
+    f.set_image("output", out)
+    f.set("hdr", True); f.set("quality", api.QUALITY_HIGH); f.set_data("weights", tza)
+    f.commit()
+    info = f.info()
+    ntiles = info["tileCountH"] * info["tileCountW"]
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for _ in range(Wm):
+      f.execute_async()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(K):
+      f.execute_async()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1) / K
+    clocks = sampler.window(t0, t1)
+    launches = K * (1 + ntiles * info["numOps"])   # autoexposure + (input, convs, output) per tile
+
+    # ---- per-op device times (same frames, CUDA events around every op) -----------------------
+    dev.set("profile", 1)
+    f.execute(); f.profile()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(K):
+      f.execute_async()
+    p1.record(stream)
+    torch.cuda.synchronize()
+    prof = f.profile()
+    dev.set("profile", 0)
+    prof_ms = p0.elapsed_time(p1) / K
+    conv_ms = sum(m for _, kind, _, m in prof if kind == 0) / K
+    in_ms = sum(m for _, kind, _, m in prof if kind == 1) / K
+    out_ms = sum(m for _, kind, _, m in prof if kind == 2) / K
+    conv_launches = sum(n for _, kind, n, _ in prof if kind == 0) // K
+    flop = weights.flops_per_pixel("base", 9) * W * H
+    conv_tf = flop / (conv_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if os.path.exists(tp):
+      try:
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
+      except Exception:
+        traffic = None
+    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (%d launches/frame)" % conv_launches,
+                "achieved": round(conv_tf, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4), "traffic": traffic,
+                "peak_source": peaks_src + ", sustained dense bf16 (kernel timed inside a long step)",
+                "frac_of_burst_peak": round(conv_tf / peaks["bf16_tflops"], 4),
+                "alg_flop_per_launch_avg": flop / max(conv_launches, 1), "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 5),
+                "conv_ms_per_frame": round(conv_ms, 4), "share_of_step": round(conv_ms / prof_ms, 4),
+                "profiled_ms_per_step": round(prof_ms, 4)}
+    px = W * H
+    passes = {
+      "input_process": {"ms": round(in_ms, 4), "alg_bytes": px * (36 + 32), "GB/s": round(px * 68 / (in_ms * 1e-3) / 1e9, 1),
+                        "frac_hbm": round(px * 68 / (in_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+      "output_process": {"ms": round(out_ms, 4), "alg_bytes": px * (32 + 12), "GB/s": round(px * 44 / (out_ms * 1e-3) / 1e9, 1),
+                         "frac_hbm": round(px * 44 / (out_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+      "conv_layers_ms": {n: round(m / K, 4) for n, kind, _, m in prof if kind == 0},
+    }
+    f.release()
+
+    # ---- end to end through the public API with pinned host buffers ---------------------------
+    e2e = None
+    if not args.no_e2e:
+      e2e = bench_e2e(api, torch, local_rank, imgs, tza, W, H, K, Wm)
+    dev.release()
+  sampler.stop()
+
+  cpu = None if args.no_cpu_baseline else cpu_port_throughput(tza, W, H)
+  line = {
+    "metric": METRIC, "value": round(px / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+    "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "dtype": "fp16 storage, fp32 accumulate", "data": "synthetic",
+    "config": dict(workload_config(args, 1), tiles="%dx%d of %dx%d" % (info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"])),
+    "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "passes": passes,
+  }
+  print(json.dumps(line))
+
+
+def bench_e2e(api, torch, gpu, imgs, tza, W, H, K, Wm):
+  """Frames arrive in pinned host memory and leave to pinned host memory: oidnWriteBufferAsync x3,
+  oidnExecuteFilterAsync, oidnReadBufferAsync per frame. Two device/filter sets (own streams)
+  alternate so the copies of one frame overlap the convolutions of the other."""
+  nb = W * H * 12
+  host_in = {k: torch.from_numpy(v).pin_memory() for k, v in imgs.items()}
+  host_out = [torch.zeros((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+  sets = []
+  for i in range(2):
+    d = api.Device((gpu,)).commit()
+    bufs = {k: d.new_buffer(nb) for k in ("color", "albedo", "normal", "output")}
+    f = d.new_filter("RT")
+    for k, b in bufs.items():
+      f.set_image(k, b, api.capi.FORMAT_FLOAT3, W, H)
+    f.set("hdr", True); f.set("quality", api.QUALITY_HIGH); f.set_data("weights", tza)
+    f.commit()
+    sets.append((d, bufs, f))
+
+  L = api.capi.lib()
+
+  def frame(i):
+    d, bufs, f = sets[i % 2]
+    for k in ("color", "albedo", "normal"):
+      L.oidnb200WriteBufferAsync(bufs[k]._h, 0, nb, host_in[k].data_ptr())
+    f.execute_async()
+    L.oidnb200ReadBufferAsync(bufs["output"]._h, 0, nb, host_out[i % 2].data_ptr())
+
+  for i in range(max(Wm, 2)):
+    frame(i)
+  for d, _, _ in sets:
+    d.sync()
+  t0 = time.perf_counter()
+  for i in range(K):
+    if i >= 2:
+      sets[i % 2][0].sync()      # the host consumes frame i-2's result before its buffers are reused
+    frame(i)
+  for d, _, _ in sets:
+    d.sync()
+  dt = (time.perf_counter() - t0) / K
+  for d, bufs, f in sets:
+    f.release()
+    for b in bufs.values():
+      b.release()
+    d.release()
+  return {"value": round(W * H / dt / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dt * 1e3, 4),
+          "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": nb,
+          "how": "pinned host fp32 images, oidnb200WriteBufferAsync x3 + ExecuteFilterAsync + ReadBufferAsync per frame, "
+                 "two device/stream sets alternating; wall clock around K frames with device sync at both ends"}
+
+
+if __name__ == "__main__":
+  main()

@@ -106,6 +106,17 @@ typedef struct oidnb200_filter_info
 } oidnb200_filter_info;
 OIDNB200_API void oidnb200GetFilterInfo(OIDNB200Filter filter, oidnb200_filter_info* info);
 
+/* Per-op device times (ms, summed over tiles and frames) since the last reset; enabled by the device
+ * parameter "profile" = 1. kind: 0 conv, 1 input process, 2 output process. Returns the op count. */
+typedef struct oidnb200_op_time
+{
+  char name[32];
+  int kind, launches;
+  double ms;
+} oidnb200_op_time;
+OIDNB200_API int oidnb200GetFilterProfile(OIDNB200Filter filter, oidnb200_op_time* out, int maxOps);
+OIDNB200_API void oidnb200ResetFilterProfile(OIDNB200Filter filter);
+
 /* The tile planner alone (no GPU needed): core/unet_filter.cpp:254-335. */
 typedef struct oidnb200_tile_plan
 {

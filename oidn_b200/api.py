@@ -226,6 +226,15 @@ class Filter:
     capi.lib().oidnb200GetFilterInfo(self._h, C.byref(i)); self._ck()
     return {n: getattr(i, n) for n, _ in capi.FilterInfo._fields_}
 
+  def profile(self, reset=True):
+    """[(name, kind, launches, ms)] per op since the last reset (device param "profile" = 1)."""
+    arr = (capi.OpTime * 64)()
+    n = capi.lib().oidnb200GetFilterProfile(self._h, arr, 64); self._ck()
+    out = [(arr[i].name.decode(), arr[i].kind, arr[i].launches, arr[i].ms) for i in range(min(n, 64))]
+    if reset:
+      capi.lib().oidnb200ResetFilterProfile(self._h)
+    return out
+
   def release(self):
     if self._h:
       capi.lib().oidnb200ReleaseFilter(self._h)

@@ -42,6 +42,10 @@ class FilterInfo(C.Structure):
                                      "largeModel", "numOps")] + [("memoryBytes", C.c_size_t)]
 
 
+class OpTime(C.Structure):
+  _fields_ = [("name", C.c_char * 32), ("kind", C.c_int), ("launches", C.c_int), ("ms", C.c_double)]
+
+
 class TilePlan(C.Structure):
   _fields_ = [(n, C.c_int) for n in ("H", "W", "tileH", "tileW", "tilePadH", "tilePadW", "tileCountH", "tileCountW",
                                      "tileAlignment", "tileOverlap")]
@@ -116,6 +120,8 @@ FILTER_ABI = {
   "oidnb200ExecuteFilter": (None, [C.c_void_p]),
   "oidnb200ExecuteFilterAsync": (None, [C.c_void_p]),
   "oidnb200GetFilterInfo": (None, [C.c_void_p, C.POINTER(FilterInfo)]),
+  "oidnb200GetFilterProfile": (C.c_int, [C.c_void_p, C.POINTER(OpTime), C.c_int]),
+  "oidnb200ResetFilterProfile": (None, [C.c_void_p]),
   "oidnb200PlanTiles": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(TilePlan)]),
   "oidnb200EnumerateTiles": (C.c_int, [C.POINTER(TilePlan), C.POINTER(C.c_int), C.c_int]),
   "oidnb200ParseTZA": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p)]),

@@ -341,8 +341,34 @@ void oidnb200GetFilterInfo(OIDNB200Filter f, oidnb200_filter_info* info)
     info->tileH = p.tileH; info->tileW = p.tileW; info->tileCountH = p.tileCountH; info->tileCountW = p.tileCountW;
     info->tileOverlap = p.tileOverlap; info->tileAlignment = p.tileAlignment;
     info->largeModel = u->isLargeModel();
+    info->numOps = u->getNumOps();
     info->memoryBytes = u->getScratchByteSize();
   });
+}
+
+int oidnb200GetFilterProfile(OIDNB200Filter f, oidnb200_op_time* out, int maxOps)
+{
+  int n = 0;
+  if (!f) return 0;
+  guarded(f->device, [&] {
+    auto* u = dynamic_cast<UNetFilter*>(f->impl.get());
+    if (!u) return;
+    const auto prof = u->getProfile();
+    n = (int)prof.size();
+    for (int i = 0; i < n && i < maxOps; ++i)
+    {
+      memset(&out[i], 0, sizeof(out[i]));
+      strncpy(out[i].name, prof[i].name.c_str(), sizeof(out[i].name) - 1);
+      out[i].kind = prof[i].kind; out[i].launches = prof[i].launches; out[i].ms = prof[i].ms;
+    }
+  });
+  return n;
+}
+
+void oidnb200ResetFilterProfile(OIDNB200Filter f)
+{
+  if (!f) return;
+  guarded(f->device, [&] { if (auto* u = dynamic_cast<UNetFilter*>(f->impl.get())) u->resetProfile(); });
 }
 
 void oidnb200PlanTiles(int H, int W, int largeModel, int deviceMinAlignment, int numEngines, long maxTilePixels,

@@ -114,6 +114,7 @@ std::shared_ptr<Filter> Device::newFilter(const std::string& type)
 void Device::setInt(const std::string& name, int value)
 {
   if (name == "verbose") verbose = value;
+  else if (name == "profile") profile = value; // backend specific: per-op CUDA-event timing
   else if (name == "maxTilePixels") maxTilePixels = value; // backend specific
   else if (committed) throw Exception(Error::InvalidOperation, "device can be committed only once");
   else throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
@@ -127,6 +128,7 @@ int Device::getInt(const std::string& name) const
   if (name == "versionMinor") return 4;
   if (name == "versionPatch") return 1;
   if (name == "verbose") return verbose;
+  if (name == "profile") return profile;
   if (name == "numSubdevices") return (int)deviceIDs.size();
   if (name == "maxTilePixels") return (int)maxTilePixels;
   if (name == "systemMemorySupported" || name == "managedMemorySupported")

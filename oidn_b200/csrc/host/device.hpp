@@ -62,6 +62,7 @@ private:
   std::vector<void*> events; // one cudaEvent_t per engine
   bool committed = false;
   int verbose = 0;
+  int profile = 0;
   long maxTilePixels;
   std::string weightsDir;
   std::mutex mutex;

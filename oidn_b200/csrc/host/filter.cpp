@@ -526,11 +526,13 @@ void UNetFilter::execute(SyncMode sync)
     inst.outputProcess->setDst(outputTemp ? outputTemp : output);
   }
 
+  const bool profiling = device->getInt("profile") != 0;
   int tileIndex = 0;
   for (const TileRect& t : tiles)
   {
     checkCancel();
     Instance& inst = instances[tileIndex % numEngines];
+    inst.graph->setProfiling(profiling);
     inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
     inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
     inst.graph->submit();
@@ -547,12 +549,17 @@ void UNetFilter::execute(SyncMode sync)
     report(device->getEngine(0));
   }
 
+  if (profiling)
+    for (auto& inst : instances) inst.graph->collectProfile(profile);
+
   if (sync == SyncMode::Blocking || progress)
   {
     device->wait();
     if (progress && progress->cancelled) throw Exception(Error::Cancelled, "execution was cancelled");
   }
 }
+
+std::vector<Graph::OpTime> UNetFilter::getProfile() { return profile; }
 
 // ------------------------------------------------------------------------------------------------
 // RTFilter (core/rt_filter.cpp)

@@ -101,6 +101,10 @@ public:
   const TilePlan& getTilePlan() const { return plan; }
   bool isLargeModel() const { return largeModel; }
   size_t getScratchByteSize() const { return totalMemoryByteSize; }
+  int getNumOps() const { return instances.empty() ? 0 : instances[0].graph->getNumOps(); }
+  // per-op device times accumulated since the last reset (device param "profile" = 1)
+  std::vector<Graph::OpTime> getProfile();
+  void resetProfile() { profile.clear(); }
 
 protected:
   virtual std::shared_ptr<TransferFunction> newTransferFunc() = 0;
@@ -165,6 +169,7 @@ private:
   bool inplace = false;
   int inplaceParam = 0;
   size_t totalMemoryByteSize = 0;
+  std::vector<Graph::OpTime> profile;
 };
 
 class RTFilter final : public UNetFilter

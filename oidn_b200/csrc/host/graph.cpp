@@ -17,6 +17,8 @@ void Graph::clear()
   inputNode = outputSrcNode = -1;
   planner.clear();
   planned = finalized = false;
+  for (const Stamp& st : stamps) { cudaEventDestroy(static_cast<cudaEvent_t>(st.e0)); cudaEventDestroy(static_cast<cudaEvent_t>(st.e1)); }
+  stamps.clear();
   privateByteSize = 0;
   if (weightBuffer) { engine->free(weightBuffer); weightBuffer = nullptr; }
 }
@@ -192,7 +194,48 @@ void Graph::submit()
 {
   if (!finalized) throw std::logic_error("graph not finalized");
   engine->makeCurrent();
-  for (auto& op : ops) op->submit();
+  if (!profiling)
+  {
+    for (auto& op : ops) op->submit();
+    return;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(engine->getStream());
+  for (size_t i = 0; i < ops.size(); ++i)
+  {
+    cudaEvent_t e0, e1;
+    checkCuda(cudaEventCreate(&e0), "cudaEventCreate");
+    checkCuda(cudaEventCreate(&e1), "cudaEventCreate");
+    cudaEventRecord(e0, st);
+    ops[i]->submit();
+    cudaEventRecord(e1, st);
+    stamps.push_back(Stamp{(int)i, e0, e1});
+  }
+}
+
+void Graph::collectProfile(std::vector<OpTime>& out)
+{
+  engine->wait();
+  if (out.size() < ops.size())
+  {
+    out.clear();
+    for (auto& op : ops)
+    {
+      int kind = 0;
+      if (dynamic_cast<InputProcess*>(op.get())) kind = 1;
+      else if (dynamic_cast<OutputProcess*>(op.get())) kind = 2;
+      out.push_back(OpTime{op->getName(), kind, 0., 0});
+    }
+  }
+  for (const Stamp& s : stamps)
+  {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(s.e0), static_cast<cudaEvent_t>(s.e1));
+    out[s.op].ms += ms;
+    out[s.op].launches += 1;
+    cudaEventDestroy(static_cast<cudaEvent_t>(s.e0));
+    cudaEventDestroy(static_cast<cudaEvent_t>(s.e1));
+  }
+  stamps.clear();
 }
 
 } // namespace oidnb200

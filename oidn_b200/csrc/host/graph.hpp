@@ -40,6 +40,13 @@ public:
   void submit();                             // launch every op in order on the engine's stream
   void clear();
 
+  // Per-op device timing (the reference's compile-time OIDN_MICROBENCH, core/graph.cpp:460-525, as
+  // a run-time switch): submit() brackets every op with CUDA events; collectProfile() waits for the
+  // stream and adds the elapsed times to `out` (one entry per op, in op order).
+  struct OpTime { std::string name; int kind; double ms; int launches; };
+  void setProfiling(bool on) { profiling = on; }
+  void collectProfile(std::vector<OpTime>& out);
+
   const std::shared_ptr<InputProcess>& getInputProcess() const { return inputProcess; }
   const std::shared_ptr<OutputProcess>& getOutputProcess() const { return outputProcess; }
   int getNumOps() const { return (int)ops.size(); }
@@ -82,6 +89,9 @@ private:
   void* scratchBase = nullptr;
   size_t scratchSize = 0;
   void* weightBuffer = nullptr;
+  bool profiling = false;
+  struct Stamp { int op; void* e0; void* e1; };
+  std::vector<Stamp> stamps;
 };
 
 } // namespace oidnb200

@@ -1,0 +1,147 @@
+"""CPU tier: host-side logic of the path -- tile scheduler, TZA parser, arena planner -- against the
+oracle's restatement of the reference and against first principles."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+from oidn_b200 import api, capi, weights
+
+SIZES = [(1, 1), (2, 2), (16, 16), (89, 257), (720, 1280), (1080, 1920), (2160, 3840), (4096, 4096), (4320, 7680),
+         (3001, 80), (80, 3001), (5000, 5000), (777, 12345)]
+
+
+@pytest.mark.parametrize("H,W", SIZES)
+@pytest.mark.parametrize("large", [False, True])
+@pytest.mark.parametrize("engines", [1, 2, 4, 8])
+def test_tile_planner_equals_reference_restatement(H, W, large, engines, oracle):
+  """oracle.plan_tiles restates core/unet_filter.cpp:254-335 line by line; ours is an independent
+  implementation of the same search."""
+  for max_px in (2160 * 2160, 3840 * 2176, 1000 * 1000):
+    ref = oracle.plan_tiles(H, W, large, 1, engines, max_px)
+    got, tiles = api.plan_tiles(H, W, large, 1, engines, max_px)
+    for k in ("tileH", "tileW", "tilePadH", "tilePadW", "tileCountH", "tileCountW", "tileOverlap", "tileAlignment"):
+      assert got[k] == ref[k], (k, got, ref)
+    check_tiles(H, W, got, tiles)
+
+
+def check_tiles(H, W, plan, tiles):
+  """Output rectangles partition the image; every input rectangle carries >= overlap context on
+  interior edges, sits 16-aligned in the tile buffer and stays inside image and buffer."""
+  cover = np.zeros((H, W), np.uint8)
+  ov = plan["tileOverlap"]
+  for t in tiles:
+    assert t["H2"] > 0 and t["W2"] > 0
+    cover[t["hDst"]:t["hDst"] + t["H2"], t["wDst"]:t["wDst"] + t["W2"]] += 1
+    assert 0 <= t["hSrc"] and t["hSrc"] + t["H1"] <= H and 0 <= t["wSrc"] and t["wSrc"] + t["W1"] <= W
+    assert t["hBuf"] >= 0 and t["hBuf"] + t["H1"] <= plan["tileH"] and t["wBuf"] >= 0 and t["wBuf"] + t["W1"] <= plan["tileW"]
+    assert t["hBuf"] % 16 == 0 and t["wBuf"] % 16 == 0 and t["hSrc"] % 16 == 0 and t["wSrc"] % 16 == 0
+    # context: distance from the output rect to the input rect edge, unless that edge is the image border
+    assert t["hDst"] - t["hSrc"] >= (ov if t["hSrc"] > 0 else 0)
+    assert (t["hSrc"] + t["H1"]) - (t["hDst"] + t["H2"]) >= (ov if t["hSrc"] + t["H1"] < H else 0)
+    assert t["wDst"] - t["wSrc"] >= (ov if t["wSrc"] > 0 else 0)
+    assert (t["wSrc"] + t["W1"]) - (t["wDst"] + t["W2"]) >= (ov if t["wSrc"] + t["W1"] < W else 0)
+    # output position inside the buffer is consistent with the input placement
+    assert t["hOutBuf"] - t["hBuf"] == t["hDst"] - t["hSrc"] and t["wOutBuf"] - t["wBuf"] == t["wDst"] - t["wSrc"]
+  assert cover.min() == 1 and cover.max() == 1
+
+
+def test_survey_tilings():
+  """SURVEY.md Appendix A (re-simulation of the reference planner)."""
+  p, t = api.plan_tiles(2160, 3840)
+  assert (p["tileW"], p["tileH"], p["tileCountW"], p["tileCountH"]) == (2016, 2160, 2, 1)
+  assert [(x["wSrc"], x["wDst"], x["W2"]) for x in t] == [(0, 0, 1920), (1824, 1920, 1920)]
+  p, _ = api.plan_tiles(4320, 7680, large=True)
+  assert (p["tileW"], p["tileH"], p["tileCountW"], p["tileCountH"], p["tileOverlap"]) == (2096, 1600, 4, 3, 112)
+  p, _ = api.plan_tiles(4320, 7680, large=True, num_engines=8)
+  assert (p["tileW"], p["tileH"], p["tileCountW"] * p["tileCountH"]) == (1472, 1248, 24)
+  p, _ = api.plan_tiles(4096, 4096)
+  assert (p["tileW"], p["tileH"], p["tileCountW"], p["tileCountH"]) == (2144, 2144, 2, 2)
+  p, _ = api.plan_tiles(1080, 1920)
+  assert (p["tileW"], p["tileH"], p["tileCountW"] * p["tileCountH"]) == (1920, 1088, 1)
+  # B200 default (4K frame = one tile)
+  p, _ = api.plan_tiles(2160, 3840, max_tile_pixels=3840 * 2176)
+  assert p["tileCountW"] * p["tileCountH"] == 1
+
+
+def parse(blob):
+  msg = C.c_char_p()
+  buf = (C.c_char * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
+  n = capi.lib().oidnb200ParseTZA(buf, len(blob), C.byref(msg))
+  return n, (msg.value or b"").decode()
+
+
+def test_tza_parser_accepts_reference_format():
+  for kind, ic, ntens in (("base", 9, 32), ("small", 3, 32), ("large", 9, 38)):
+    blob = weights.model_tza(kind, ic)
+    assert parse(blob) == (ntens, "")
+    back = weights.read_tza(blob)
+    for name, t in weights.make_weights(kind, ic).items():
+      np.testing.assert_array_equal(back[name], t)
+
+
+def test_tza_parser_rejects_malformed_blobs():
+  """Messages and error class of core/tza.cpp:27-103 (all Error::InvalidOperation = 3)."""
+  blob = bytearray(weights.model_tza("small", 3))
+  assert parse(b"") == (-3, "invalid or corrupted weights blob")
+  assert parse(bytes(blob[:11]))[0] == -3
+  bad = bytearray(blob); bad[0] ^= 0xFF
+  assert parse(bytes(bad)) == (-3, "invalid or corrupted weights blob")
+  bad = bytearray(blob); bad[2] = 3
+  assert parse(bytes(bad)) == (-3, "unsupported weights blob version")
+  bad = bytearray(blob); struct.pack_into("<Q", bad, 4, len(blob) + 1)
+  assert parse(bytes(bad))[0] == -3
+  assert parse(bytes(blob[:-9]))[0] == -3                    # truncated table
+  table = struct.unpack_from("<Q", blob, 4)[0]
+  # first table entry: u32 n, u16 len, name, u8 ndims, dims, layout, dtype, u64 offset
+  ln = struct.unpack_from("<H", blob, table + 4)[0]
+  nd_off = table + 6 + ln
+  nd = blob[nd_off]
+  layout_off = nd_off + 1 + 4 * nd
+  bad = bytearray(blob); bad[layout_off] = ord("q")
+  assert parse(bytes(bad)) == (-3, "invalid tensor layout")
+  bad = bytearray(blob); bad[layout_off + nd] = ord("d")
+  assert parse(bytes(bad)) == (-3, "invalid tensor data type")
+  bad = bytearray(blob); struct.pack_into("<Q", bad, layout_off + nd + 1, len(blob) - 2)
+  assert parse(bytes(bad))[0] == -3                           # tensor data runs past the blob
+
+
+def plan_arena(sizes, first, last):
+  n = len(sizes)
+  off = (C.c_size_t * n)()
+  total = capi.lib().oidnb200PlanArena(n, (C.c_size_t * n)(*sizes), (C.c_int * n)(*first), (C.c_int * n)(*last), off)
+  return total, list(off)
+
+
+def test_arena_planner_packs_lifetimes():
+  # a chain a->b->c->d where only neighbours overlap in time: two slots suffice
+  total, off = plan_arena([1000, 1000, 1000, 1000], [0, 1, 2, 3], [1, 2, 3, 4])
+  assert total != 2**64 - 1 and total <= 2 * 1024
+  assert all(o % 256 == 0 for o in off)
+  # random lifetimes: never overlapping in space and time at once (validated inside), never worse than the sum
+  rng = np.random.default_rng(0)
+  for _ in range(50):
+    n = int(rng.integers(2, 40))
+    sizes = [int(s) for s in rng.integers(1, 1 << 20, n)]
+    first = [int(v) for v in rng.integers(0, 30, n)]
+    last = [f + int(v) for f, v in zip(first, rng.integers(0, 10, n))]
+    total, off = plan_arena(sizes, first, last)
+    assert total != 2**64 - 1, "planner produced overlapping live allocations"
+    assert total <= sum((s + 255) // 256 * 256 for s in sizes)
+    live_peak = max(sum(s for s, f, l in zip(sizes, first, last) if f <= t <= l) for t in range(41))
+    assert total >= live_peak
+
+
+def test_unet_arena_is_close_to_the_live_peak():
+  """Tensors of the fused base UNet at a 1920x1088 tile: the planner's total must
+  be within 15 % of the peak live set (in + d2b + d1a ~ 0.40 GB)."""
+  px = 1920 * 1088
+  def b(c, s): return px // (s * s) * c * 2
+  # (bytes, producer op, last consumer op) in graph order: input=0, convs 1..16, output=17
+  t = [(b(16, 1), 0, 14), (b(32, 1), 1, 2), (b(32, 2), 2, 12), (b(48, 4), 3, 10), (b(64, 8), 4, 8), (b(80, 16), 5, 6),
+       (b(96, 16), 6, 7), (b(96, 16), 7, 8), (b(112, 8), 8, 9), (b(112, 8), 9, 10), (b(96, 4), 10, 11), (b(96, 4), 11, 12),
+       (b(64, 2), 12, 13), (b(64, 2), 13, 14), (b(64, 1), 14, 15), (b(32, 1), 15, 16), (b(16, 1), 16, 17)]
+  total, _ = plan_arena([x[0] for x in t], [x[1] for x in t], [x[2] for x in t])
+  peak = max(sum(s for s, f, l in t if f <= op <= l) for op in range(18))
+  assert peak <= total <= 1.15 * peak, (total, peak)

@@ -160,9 +160,9 @@ def test_input_process_vectorised_path_equals_generic(oracle):
 @pytest.mark.parametrize("fmt", [("float32", 3), ("float16", 3), ("float32", 1), ("float16", 2)])
 def test_output_process(tf, hdr, snorm, fmt, oracle):
   dtype, Cout = fmt
-  TH, TW, C = 48, 128, 16
+  TH, TW, CT = 48, 128, 16
   rng = np.random.default_rng(3)
-  src = np.zeros((TH, TW, C), np.float16)
+  src = np.zeros((TH, TW, CT), np.float16)
   src[:, :, :3] = _rand_half(rng, (TH, TW, 3), -0.1, 1.0)
   src[2, 3, 0] = np.nan; src[2, 4, 1] = np.inf
   tile = dict(hSrcBegin=16, wSrcBegin=32, hDstBegin=5, wDstBegin=8, H=30, W=92)
@@ -173,12 +173,12 @@ def test_output_process(tf, hdr, snorm, fmt, oracle):
   oi = oracle.image_of(ref)
   ot = oracle.Tile(*[tile[n] for n, _ in oracle.Tile._fields_])
   s32 = src.astype(np.float32)
-  oracle.lib().oro_output_process(s32.ctypes.data, TH, TW, C, C.byref(ot), tf, hdr, snorm, scale, C.byref(oi))
+  oracle.lib().oro_output_process(s32.ctypes.data, TH, TW, CT, C.byref(ot), tf, hdr, snorm, scale, C.byref(oi))
   gi = image_of(got_t)
   gt = capi.Tile(*[tile[n] for n, _ in capi.Tile._fields_])
   gtf = capi.Transfer(tf, scale, None)
   s = torch.from_numpy(src).cuda()
-  check(capi.lib().oidnb200_output_process_launch(s.data_ptr(), TH, TW, C, C.byref(gt), C.byref(gtf), hdr, snorm, C.byref(gi),
+  check(capi.lib().oidnb200_output_process_launch(s.data_ptr(), TH, TW, CT, C.byref(gt), C.byref(gtf), hdr, snorm, C.byref(gi),
                                                   torch.cuda.current_stream().cuda_stream))
   got = got_t.cpu().numpy().astype(np.float32)
   r = ref.astype(np.float32)
