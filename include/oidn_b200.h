@@ -70,6 +70,11 @@ OIDNB200_API void oidnb200WriteBuffer(OIDNB200Buffer buffer, size_t byteOffset, 
 OIDNB200_API void oidnb200ReadBufferAsync(OIDNB200Buffer buffer, size_t byteOffset, size_t byteSize, void* dstHostPtr);
 OIDNB200_API void oidnb200WriteBufferAsync(OIDNB200Buffer buffer, size_t byteOffset, size_t byteSize, const void* srcHostPtr);
 OIDNB200_API void oidnb200ReleaseBuffer(OIDNB200Buffer buffer);
+/* Cross-process sharing of a device buffer on one node (the role oidnNewSharedBufferFromFD,
+ * oidn.h:326-329, plays for external memory): the owner exports a 64-byte CUDA IPC handle, a peer
+ * process imports it as a buffer it may read and write over NVLink. Device-storage buffers only. */
+OIDNB200_API void oidnb200GetBufferIpcHandle(OIDNB200Buffer buffer, void* outHandle64);
+OIDNB200_API OIDNB200Buffer oidnb200NewSharedBufferFromIpcHandle(OIDNB200Device device, const void* handle64, size_t byteSize);
 
 /* ---- filters ------------------------------------------------------------------------------ */
 OIDNB200_API OIDNB200Filter oidnb200NewFilter(OIDNB200Device device, const char* type); /* "RT" | "RTLightmap", oidn.h:392 */

@@ -82,6 +82,12 @@ class Device:
     h = capi.lib().oidnb200NewBufferWithStorage(self._h, byte_size, storage); _check(self._h)
     return Buffer(self, h)
 
+  def import_buffer(self, ipc_handle, byte_size):
+    """Opens a peer process's exported device buffer (CUDA IPC, same node)."""
+    raw = (C.c_char * 64).from_buffer_copy(bytes(ipc_handle))
+    h = capi.lib().oidnb200NewSharedBufferFromIpcHandle(self._h, raw, byte_size); _check(self._h)
+    return Buffer(self, h)
+
   def release(self):
     if self._h:
       capi.lib().oidnb200ReleaseDevice(self._h)
@@ -105,6 +111,11 @@ class Buffer:
   @property
   def size(self):
     return capi.lib().oidnb200GetBufferSize(self._h)
+
+  def ipc_handle(self):
+    raw = (C.c_char * 64)()
+    capi.lib().oidnb200GetBufferIpcHandle(self._h, raw); _check(self.device._h)
+    return bytes(raw)
 
   def write(self, array, byte_offset=0, sync=True):
     a = np.ascontiguousarray(array)
@@ -181,6 +192,10 @@ class Filter:
       self._keep["data:" + name] = buf
       capi.lib().oidnb200SetSharedFilterData(self._h, name.encode(), C.addressof(buf), len(data))
     self._ck()
+
+  def set_input_scale_ptr(self, dev_ptr):
+    """Backend extension for sharded execution: the input scale is read from this device float."""
+    capi.lib().oidnb200SetSharedFilterData(self._h, b"inputScalePtr", dev_ptr, 4 if dev_ptr else 0); self._ck()
 
   def update_data(self, name):
     capi.lib().oidnb200UpdateFilterData(self._h, name.encode()); self._ck()

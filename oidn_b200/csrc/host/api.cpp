@@ -22,6 +22,7 @@ struct oidnb200_buffer_t
   void* ptr = nullptr;
   size_t size = 0;
   Storage storage = Storage::Device;
+  bool imported = false; // opened from a CUDA IPC handle
 };
 
 struct oidnb200_filter_t
@@ -200,10 +201,47 @@ void oidnb200ReleaseBuffer(OIDNB200Buffer b)
   if (b->refs.fetch_sub(1) == 1)
   {
     oidnb200_device_t* d = b->device;
-    guarded(d, [&] { d->impl->wait(); d->impl->getEngine(0)->free(b->ptr, b->storage); });
+    guarded(d, [&] {
+      d->impl->wait();
+      if (b->imported) { d->impl->getEngine(0)->makeCurrent(); cudaIpcCloseMemHandle(b->ptr); }
+      else d->impl->getEngine(0)->free(b->ptr, b->storage);
+    });
     delete b;
     releaseDevice(d);
   }
+}
+
+void oidnb200GetBufferIpcHandle(OIDNB200Buffer b, void* outHandle64)
+{
+  if (!b) return;
+  guarded(b->device, [&] {
+    if (!outHandle64) throw Exception(Error::InvalidArgument, "handle pointer is null");
+    if (b->storage != Storage::Device || b->imported)
+      throw Exception(Error::InvalidOperation, "only device-storage buffers owned by this process can be exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    b->device->impl->getEngine(0)->makeCurrent();
+    checkCuda(cudaIpcGetMemHandle(&h, b->ptr), "cudaIpcGetMemHandle");
+    memcpy(outHandle64, &h, 64);
+  });
+}
+
+OIDNB200Buffer oidnb200NewSharedBufferFromIpcHandle(OIDNB200Device d, const void* handle64, size_t byteSize)
+{
+  oidnb200_buffer_t* b = nullptr;
+  guarded(d, [&] {
+    d->impl->checkCommitted();
+    if (!handle64) throw Exception(Error::InvalidArgument, "handle pointer is null");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    d->impl->getEngine(0)->makeCurrent();
+    checkCuda(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    b = new oidnb200_buffer_t();
+    b->device = d; b->ptr = p; b->size = byteSize; b->storage = Storage::Device; b->imported = true;
+    retainDevice(d);
+  });
+  return b;
 }
 
 // ---- filters ----------------------------------------------------------------------------------

@@ -118,7 +118,13 @@ static void warnUnknown(Device* device, const std::string& name)
 
 void UNetFilter::setData(const std::string& name, const Data& data)
 {
-  if (name == "weights") setParam(userWeightsBlob, data); else warnUnknown(device, name);
+  if (name == "weights") setParam(userWeightsBlob, data);
+  else if (name == "inputScalePtr")
+  {
+    if (data && data.size < sizeof(float)) throw Exception(Error::InvalidArgument, "inputScalePtr must point to one float");
+    inputScaleDevPtr = static_cast<const float*>(data.ptr); // device memory, dereferenced by the kernels only
+  }
+  else warnUnknown(device, name);
   dirty = true;
 }
 
@@ -130,7 +136,9 @@ void UNetFilter::updateData(const std::string& name)
 
 void UNetFilter::unsetData(const std::string& name)
 {
-  if (name == "weights") removeParam(userWeightsBlob); else warnUnknown(device, name);
+  if (name == "weights") removeParam(userWeightsBlob);
+  else if (name == "inputScalePtr") inputScaleDevPtr = nullptr;
+  else warnUnknown(device, name);
   dirty = true;
 }
 
@@ -145,6 +153,16 @@ void UNetFilter::setInt(const std::string& name, int value)
     setParam(quality, q);
   }
   else if (name == "maxMemoryMB") setParam(maxMemoryMB, value);
+  else if (name == "numShards")
+  {
+    if (value < 1) throw Exception(Error::InvalidArgument, "numShards must be >= 1");
+    setParam(numShards, value);
+  }
+  else if (name == "shardIndex")
+  {
+    if (value < 0) throw Exception(Error::InvalidArgument, "shardIndex must be >= 0");
+    setParam(shardIndex, value);
+  }
   else warnUnknown(device, name);
   dirty = true;
 }
@@ -153,6 +171,8 @@ int UNetFilter::getInt(const std::string& name)
 {
   if (name == "quality") return static_cast<int>(quality);
   if (name == "maxMemoryMB") return maxMemoryMB;
+  if (name == "numShards") return numShards;
+  if (name == "shardIndex") return shardIndex;
   if (name == "tileAlignment" || name == "alignment") return plan.tileAlignment;
   if (name == "tileOverlap" || name == "overlap") return plan.tileOverlap;
   throw Exception(Error::InvalidArgument, "unknown filter parameter or type mismatch: '" + name + "'");
@@ -226,6 +246,7 @@ void UNetFilter::checkParams()
   if (directional && (hdr || srgb))
     throw Exception(Error::InvalidOperation, "directional and hdr/srgb modes cannot be enabled at the same time");
   if (hdr && srgb) throw Exception(Error::InvalidOperation, "hdr and srgb modes cannot be enabled at the same time");
+  if (shardIndex >= numShards) throw Exception(Error::InvalidOperation, "shardIndex must be smaller than numShards");
 }
 
 // Reads <weightsDir>/<stem>.tza; a missing file or a Git-LFS pointer counts as "model not available".
@@ -442,7 +463,7 @@ void UNetFilter::init()
   const long maxTilePixels = maxMemoryMB < 0 ? device->getMaxTilePixels() : LONG_MAX;
   const size_t maxMemoryByteSize = maxMemoryMB >= 0 ? (size_t)maxMemoryMB * 1024 * 1024 : SIZE_MAX;
 
-  plan = planTiles(H, W, largeModel, device->getMinTileAlignment(), device->getNumEngines(), maxTilePixels,
+  plan = planTiles(H, W, largeModel, device->getMinTileAlignment(), device->getNumEngines() * numShards, maxTilePixels,
                    [&](const TilePlan& c) { return buildModel(c, maxMemoryByteSize, false); });
   if (!buildModel(plan, SIZE_MAX, true)) throw std::runtime_error("could not build filter model");
   tiles = enumerateTiles(plan);
@@ -488,7 +509,8 @@ void UNetFilter::execute(SyncMode sync)
   {
     progress = std::make_shared<ProgressState>();
     progress->func = progressFunc; progress->userPtr = progressUserPtr;
-    progress->total = (double)tiles.size() + ((hdr && std::isnan(inputScale)) ? 1 : 0) + (outputTemp ? 1 : 0);
+    progress->total = (double)((tiles.size() + numShards - 1 - shardIndex) / numShards) +
+                      ((hdr && std::isnan(inputScale) && !inputScaleDevPtr) ? 1 : 0) + (outputTemp ? 1 : 0);
     if (!progressFunc(progressUserPtr, 0.)) throw Exception(Error::Cancelled, "execution was cancelled");
   }
   auto report = [&](Engine* e) {
@@ -503,7 +525,9 @@ void UNetFilter::execute(SyncMode sync)
   };
 
   // input scale (core/unet_filter.cpp:172-189)
-  if (std::isnan(inputScale))
+  if (inputScaleDevPtr)
+    transferFunc->setInputScale(inputScaleDevPtr);
+  else if (std::isnan(inputScale))
   {
     if (hdr)
     {
@@ -527,9 +551,10 @@ void UNetFilter::execute(SyncMode sync)
   }
 
   const bool profiling = device->getInt("profile") != 0;
-  int tileIndex = 0;
+  int tileIndex = 0, globalIndex = 0;
   for (const TileRect& t : tiles)
   {
+    if (globalIndex++ % numShards != shardIndex) continue; // another process's tile
     checkCancel();
     Instance& inst = instances[tileIndex % numEngines];
     inst.graph->setProfiling(profiling);

@@ -136,6 +136,12 @@ protected:
   float inputScale;
   Quality quality = defaultQuality;
   int maxMemoryMB = -1;
+  // Multi-process tile sharding (one process per GPU): this filter instance executes the tiles
+  // whose index % numShards == shardIndex of the common plan, and reads the input scale from a
+  // device pointer the caller keeps up to date (e.g. broadcast from the rank that ran the
+  // autoexposure). Backend-specific parameters "numShards", "shardIndex", data "inputScalePtr".
+  int numShards = 1, shardIndex = 0;
+  const float* inputScaleDevPtr = nullptr;
 
 private:
   void init();

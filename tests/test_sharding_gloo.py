@@ -1,0 +1,68 @@
+"""CPU tier, world_size 2 over gloo: the host-side plumbing of the multi-process tile sharding --
+every rank derives the same plan, the ranks' tile sets partition the frame, the handle exchange and
+the frame join run over the process group."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+  return p
+
+
+def _worker(rank, world, port, q):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from oidn_b200 import sharded
+  out = {}
+  for (H, W, large) in ((4320, 7680, False), (4320, 7680, True), (2160, 3840, False), (1000, 3000, False)):
+    plan, mine = sharded.tiles_of_rank(H, W, large, world, rank)
+    # every rank must see the same plan
+    plans = [None] * world
+    dist.all_gather_object(plans, plan)
+    assert all(p == plans[0] for p in plans)
+    assert (plan["tileCountH"] * plan["tileCountW"]) % world == 0
+    cover = np.zeros((H, W), np.int32)
+    for t in mine:
+      cover[t["hDst"]:t["hDst"] + t["H2"], t["wDst"]:t["wDst"] + t["W2"]] += 1
+    total = torch.from_numpy(cover)
+    dist.all_reduce(total)                     # the join: all ranks' rectangles together
+    assert int(total.min()) == 1 and int(total.max()) == 1, "ranks' output rectangles must partition the frame"
+    out[(H, W, large)] = len(mine)
+  # handle exchange: rank 0's 64-byte handles reach every rank unchanged
+  handles = {"color": bytes(range(64)), "output": bytes(range(64, 128))} if rank == 0 else None
+  got = sharded.broadcast_object(dist, handles, 0)
+  assert got["color"] == bytes(range(64)) and got["output"] == bytes(range(64, 128))
+  # scale broadcast + join token, as in ShardedFilter.execute_async
+  scale = torch.tensor([0.125 if rank == 0 else -1.0])
+  dist.broadcast(scale, src=0)
+  assert float(scale) == 0.125
+  q.put((rank, out))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_world_size_2_tile_sharding():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=180) for _ in procs]
+  for p in procs:
+    p.join(60)
+    assert p.exitcode == 0
+  counts = dict(res)
+  assert counts[0] == counts[1], "round-robin dealing gives both ranks the same number of tiles"
