@@ -21,7 +21,7 @@ class ConvDesc(C.Structure):
 
 class ConvInfo(C.Structure):
   _fields_ = [(n, C.c_int) for n in ("grid", "smem_bytes", "ngroups", "cout_group", "nchunks", "nstages", "ring_slots",
-                                     "rows_per_item", "nstrips", "nrowchunks", "nstreams")]
+                                     "rows_per_item", "nstrips", "nrowchunks", "nstreams", "out_nbuf")]
 
 
 class Image(C.Structure):
@@ -66,6 +66,7 @@ KERNEL_ABI = {
   "oidnb200_conv_bind": (C.c_int, [C.c_void_p] * 6),
   "oidnb200_conv_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
   "oidnb200_conv_launch_simt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+  "oidnb200_conv_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
   "oidnb200_conv_get_info": (C.c_int, [C.c_void_p, C.POINTER(ConvInfo)]),
   "oidnb200_input_process_launch": (C.c_int, [C.POINTER(Image), C.POINTER(Image), C.POINTER(Image), C.POINTER(Tile),
                                               C.POINTER(Transfer), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,

@@ -16,11 +16,11 @@ namespace oidnb200 {
 
 constexpr int kMaxChunks   = 8;     // K chunks (<=64 channels each) over both sources
 constexpr int kMaxOutChunks = 3;    // output-channel pieces (64/32/16) of one CoutG group
-constexpr int kMaxStages   = 8;     // A-operand pipeline depth
+constexpr int kMaxStages   = 24;    // A-operand pipeline depth (per stream)
 constexpr int kConvThreads = 384;   // 2 x (TMA warp + MMA warp) + 2 x 4 epilogue warps
 constexpr int kStripW      = 128;   // output pixels per MMA tile (UMMA M)
-constexpr int kStageBytes  = 17408; // one A stage: up to 132 px x 128 B, 1024-aligned
-constexpr int kSmemHeader  = 2048;  // barriers + TMEM pointer + bias
+constexpr int kMaxStageBytes = 17408; // one A stage: up to 132 px x 128 B, 1024-aligned (64-channel chunk)
+constexpr int kSmemHeader  = 2048;  // barriers + TMEM pointer (1.5 KB) + bias (512 B)
 constexpr int kTmemCols    = 512;
 constexpr int kMaxSlots    = 16;
 constexpr int kSmemBudget  = 232448; // 227 KB opt-in dynamic shared memory per CTA
@@ -45,16 +45,18 @@ struct ConvKernelParams
   int      R;                       // TMEM accumulator ring slots per stream (nstreams*R*CoutG <= 512)
   int      RC, nstrips, nrowchunks; // rows per work item, strips across W, row chunks down H
   int      nstages;                 // A pipeline stages per stream
+  uint32_t stage_bytes;             // bytes of one A stage: 132 px x the widest K chunk, 1024-aligned
   uint32_t w_bytes;                 // total weight bytes TMA-loaded per CTA
   uint32_t b_bytes;                 // size of the resident weight region (1024-aligned blocks)
   int      nout;                    // output pieces of the group
   int      out_c0[kMaxOutChunks];   // first channel of the piece inside the group
   int      out_cc[kMaxOutChunks];   // channels in the piece (64/32/16)
-  uint32_t out_off[kMaxOutChunks];  // byte offset of the piece inside one staging buffer
-  uint32_t out_buf_bytes;           // bytes of one staging buffer
-  int      out_nbuf;                // 1 or 2 staging buffers per epilogue warpgroup (two warpgroups)
+  uint32_t out_off[kMaxOutChunks];  // byte offset of the piece inside one staging slice
+  uint32_t out_buf_bytes;           // bytes of one staging slice (one warp, one row)
+  int      out_nbuf;                // 1 or 2 staging slices per epilogue warp (8 warps)
   int      relu, post_op;
   const float* bias;                // fp32 [CoutAlloc]
+  unsigned long long* trace;        // [12 warps][8 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
 };
 
 } // namespace oidnb200

@@ -159,7 +159,13 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
 
   // Output-channel group: the largest one whose resident weights + output staging leave room for
   // at least two A stages.
-  const uint32_t stage_bytes = (uint32_t)kStageBytes;
+  // One A stage holds one input row of one K chunk: 132 pixels (130 + the 2 extra of an upsampled
+  // source) x the widest chunk. Narrow layers get small stages, hence a deep TMA prefetch ring:
+  // keeping HBM busy needs ~10 MB of loads in flight chip-wide (bandwidth x latency).
+  int maxcc = 16;
+  for (int c = 0; c < n; ++c) maxcc = std::max(maxcc, kp.chunk_cc[c]);
+  const uint32_t stage_bytes = align_up(132u * maxcc * 2u, 1024);
+  kp.stage_bytes = stage_bytes;
   const int min_stages = 2;
   const uint32_t avail = kSmemBudget - 1024 /*alignment slack*/ - kSmemHeader;
   auto b_bytes = [&](int CoutG) {
@@ -168,20 +174,23 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
       off = align_up(off, 1024) + 3u * (3u * CoutG * kp.chunk_cc[c] * 2u);
     return align_up(off, 1024);
   };
-  const uint32_t out_px = (d.post_op == POST_POOL) ? 64u : 128u;
-  auto out_bytes = [&](int CoutG) { // one staging buffer: pieces of 64/32/16 channels, 1024-aligned
+  // Output staging: every epilogue warp (2 warpgroups x 4) owns a slice for its 32 pixels (16 after
+  // pooling), cut into pieces of 64/32/16 channels, each piece 1024-aligned (swizzle atoms).
+  const uint32_t out_rows = (d.post_op == POST_POOL) ? 16u : 32u;
+  auto out_bytes = [&](int CoutG) { // one staging slice of one warp
     uint32_t off = 0;
     for (int rem = CoutG; rem > 0;)
     {
       const int cc = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
-      off = align_up(off, 1024) + out_px * cc * 2u;
+      off = align_up(off, 1024) + out_rows * cc * 2u;
       rem -= cc;
     }
     return align_up(off, 1024);
   };
+  constexpr uint32_t kEpiWarps = 8;
   int CoutG = std::min(d.Cout, 128);
-  while (CoutG > 16 && b_bytes(CoutG) + 2 * out_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
-  if (b_bytes(CoutG) + 2 * out_bytes(CoutG) + min_stages * stage_bytes > avail)
+  while (CoutG > 16 && b_bytes(CoutG) + kEpiWarps * out_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
+  if (b_bytes(CoutG) + kEpiWarps * out_bytes(CoutG) + min_stages * stage_bytes > avail)
   {
     set_error("conv: weights for 16 output channels do not fit in shared memory");
     return OIDNB200_ERR_UNSUPPORTED;
@@ -215,21 +224,36 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
     kp.out_c0[kp.nout] = c0;
     kp.out_cc[kp.nout] = cc;
     kp.out_off[kp.nout] = ooff;
-    ooff += out_px * cc * 2u;
+    ooff += out_rows * cc * 2u;
     c0 += cc; rem -= cc; kp.nout++;
   }
   kp.out_buf_bytes = align_up(ooff, 1024);
 
-  // What is left after weights and one staging buffer per epilogue warpgroup goes to A stages.
-  // Two streams need a 4-slot accumulator ring each (CoutG <= 64) and >= 2 stages each.
-  uint32_t left = avail - bbytes - 2 * kp.out_buf_bytes;
-  kp.out_nbuf = 1;
-  int total_stages = (int)(left / stage_bytes);
-  kp.nstreams = (CoutG <= 64 && total_stages >= 4) ? 2 : 1;
-  kp.nstages = std::min(total_stages / kp.nstreams, kMaxStages);
+  // What is left after the weights and the staging slices goes to A stages. Two streams need a
+  // 4-slot accumulator ring each (CoutG <= 64) and >= 2 stages each. Staging is double-buffered
+  // (a warp's store of row i overlaps its work on row i+1) unless that would cost a stream or
+  // leave fewer than 3 stages per stream.
+  auto config = [&](int nbuf, int& nstreams, int& nstages) {
+    const uint32_t left = avail - bbytes - kEpiWarps * nbuf * kp.out_buf_bytes;
+    const int total_stages = (int)(left / stage_bytes);
+    nstreams = (CoutG <= 64 && total_stages >= 4) ? 2 : 1;
+    nstages = std::min(total_stages / nstreams, kMaxStages);
+  };
+  int ns1, st1, ns2 = 0, st2 = 0;
+  config(1, ns1, st1);
+  const bool fits2 = bbytes + kEpiWarps * 2 * kp.out_buf_bytes + min_stages * stage_bytes <= avail;
+  if (fits2) config(2, ns2, st2);
+  if (fits2 && ns2 == ns1 && st2 >= std::min(3, st1))
+  {
+    kp.out_nbuf = 2; kp.nstreams = ns2; kp.nstages = st2;
+  }
+  else
+  {
+    kp.out_nbuf = 1; kp.nstreams = ns1; kp.nstages = st1;
+  }
   kp.R = std::min(kMaxSlots, (kTmemCols / kp.nstreams) / CoutG);
   pl.smem = 1024 + kSmemHeader + (size_t)kp.nstreams * kp.nstages * stage_bytes + bbytes +
-            (size_t)2 * kp.out_nbuf * kp.out_buf_bytes;
+            (size_t)kEpiWarps * kp.out_nbuf * kp.out_buf_bytes;
 
   // Work decomposition: strips of 128 px x RC rows; pick RC minimising the critical path.
   kp.H = d.H; kp.W = d.W;
@@ -306,7 +330,7 @@ static int plan_bind(ConvPlan& pl, const void* src1, const void* src2, const voi
     const uint64_t os[2] = {(uint64_t)d.Cout * 2, Wd * d.Cout * 2};
     for (int oc = 0; oc < kp.nout; ++oc)
     {
-      const uint32_t ob[3] = {(uint32_t)kp.out_cc[oc], d.post_op == POST_POOL ? 64u : 128u, 1};
+      const uint32_t ob[3] = {(uint32_t)kp.out_cc[oc], d.post_op == POST_POOL ? 16u : 32u, 1}; // one warp's pixels
       const int rc = encode_tmap(&kp.omap[oc], dst, 3, od, os, ob, kp.out_cc[oc]);
       if (rc) return rc;
     }
@@ -525,6 +549,12 @@ int oidnb200_conv_launch_simt(const oidnb200_conv* conv, void* scratch, oidnb200
   return 0;
 }
 
+int oidnb200_conv_set_trace(oidnb200_conv* conv, void* trace_counters)
+{
+  conv->plan.kp.trace = static_cast<unsigned long long*>(trace_counters);
+  return 0;
+}
+
 int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info)
 {
   const ConvPlan& pl = conv->plan;
@@ -539,6 +569,7 @@ int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info)
   info->nstrips = pl.kp.nstrips;
   info->nrowchunks = pl.kp.nrowchunks;
   info->nstreams = pl.kp.nstreams;
+  info->out_nbuf = pl.kp.out_nbuf;
   return 0;
 }
 

@@ -38,6 +38,21 @@ namespace oidnb200 {
 
 using namespace ptx;
 
+// Optional wait-time tracing (build with -DOIDN_B200_TRACE, tools/probe_conv --trace): every role
+// accumulates the cycles it spends blocked at each barrier; lane 0 adds them to p.trace[warp][tag].
+#ifdef OIDN_B200_TRACE
+#define TRACE_DECL long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_start = clock64();
+#define MBAR_WAIT(bar, par, tag) do { const long long t0_ = clock64(); mbar_wait(bar, par, tag); tr[tag] += clock64() - t0_; } while (0)
+#define TRACE_WRAP(tag, stmt) do { const long long t0_ = clock64(); stmt; tr[tag] += clock64() - t0_; } while (0)
+#define TRACE_FLUSH() do { if (p.trace && lane == 0) { tr[0] = clock64() - tr_start; \
+  for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&p.trace[warp * 8 + i_], (unsigned long long)tr[i_]); } } while (0)
+#else
+#define TRACE_DECL
+#define MBAR_WAIT(bar, par, tag) mbar_wait(bar, par, tag)
+#define TRACE_WRAP(tag, stmt) stmt
+#define TRACE_FLUSH()
+#endif
+
 namespace {
 
 struct SmemLayout
@@ -49,10 +64,10 @@ struct SmemLayout
   static constexpr uint32_t tmem_full  = w_full + 8;                         // 2 x kMaxSlots x 8
   static constexpr uint32_t tmem_empty = tmem_full + 2 * 8 * kMaxSlots;
   static constexpr uint32_t tmem_ptr   = tmem_empty + 2 * 8 * kMaxSlots;
-  static constexpr uint32_t bias       = 1024;                               // 128 floats
+  static constexpr uint32_t bias       = 1536;                               // 128 floats
   static constexpr uint32_t a_ring     = kSmemHeader;
 };
-static_assert(SmemLayout::tmem_ptr + 4 <= 1024, "barrier block overflows");
+static_assert(SmemLayout::tmem_ptr + 4 <= SmemLayout::bias && SmemLayout::bias + 512 <= kSmemHeader, "barrier block overflows");
 
 struct Item
 {
@@ -116,6 +131,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  TRACE_DECL
 
   const int NST     = p.nstreams;               // 1 or 2
   const int group   = blockIdx.x % p.ngroups;
@@ -124,7 +140,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   const int nitems  = p.nstrips * p.nrowchunks;
   const int NS      = p.nstages;                // A stages per stream
   const int R       = p.R;                      // accumulator ring slots per stream
-  const uint32_t stage_bytes = (uint32_t)kStageBytes;
+  const uint32_t stage_bytes = p.stage_bytes;
   const uint32_t b_region = sbase + SmemLayout::a_ring + (uint32_t)(NST * NS) * stage_bytes;
 
   // ---------------------------------------------------------------- setup
@@ -201,7 +217,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
             {
               const uint32_t full = full_a + 8 * s;
               const uint32_t dst  = a_ring + s * stage_bytes;
-              mbar_wait(empty_a + 8 * s, ph ^ 1, 1);
+              MBAR_WAIT(empty_a + 8 * s, ph ^ 1, 1);
               const int cc = p.chunk_cc[c];
               if (leader)
               {
@@ -237,7 +253,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
         const uint32_t tbase = tmem_base + (uint32_t)st * (uint32_t)R * CoutG; // this stream's columns
         const uint32_t max_run = min(3u, 256u / CoutG);
         const uint32_t idesc1 = umma_idesc_f16(CoutG);
-        mbar_wait(sbase + SmemLayout::w_full, 0, 2);
+        MBAR_WAIT(sbase + SmemLayout::w_full, 0, 2);
         tc_fence_after();
         uint32_t stage = 0, sphase = 0;       // A ring position / parity
         uint32_t a_mod = 0, a_par = 0;        // (first accumulator index of the item) % R, parity of / R
@@ -254,7 +270,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
             if (fresh)
             {
               // kh=0 opens a fresh accumulator: its ring slot must have been drained.
-              mbar_wait(tempty + 8 * ((R - 1) - top_mod), top_par ^ 1, 3);
+              MBAR_WAIT(tempty + 8 * ((R - 1) - top_mod), top_par ^ 1, 3);
               tc_fence_after();
             }
             // Split kh_lo..kh_hi into (at most two) runs contiguous in TMEM (ring wrap), N <= 256.
@@ -292,7 +308,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
               const uint32_t bblk16 = p.chunk_bblk[c] >> 4;
               const uint32_t rb0 = brow0 * row16, rb1 = brow1 * row16;
               const bool first = fresh && c == 0;
-              mbar_wait(full_a + 8 * stage, sphase, 4);
+              MBAR_WAIT(full_a + 8 * stage, sphase, 4);
               tc_fence_after();
               if (leader)
               {
@@ -345,27 +361,26 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   {
     // Two warpgroups of 128 threads = the 128 TMEM lanes (pixels) of an accumulator. With two
     // streams, warpgroup g drains every row of stream g; with one stream the two warpgroups drain
-    // alternate rows (row pairs when pooling). Per row:
-    // TMEM -> registers -> +bias (fp32) -> fp16 -> ReLU -> swizzled smem staging -> TMA store.
+    // alternate rows (row pairs when pooling). Every WARP is its own store pipeline: it owns the 32
+    // pixels of its TMEM lane quarter, stages them in its own (double-buffered) swizzled smem
+    // slice and issues its own TMA store, so a row costs no CTA-level barrier:
+    // TMEM -> registers -> +bias (fp32) -> fp16 -> ReLU -> (2x2 max) -> smem slice -> TMA store.
     const int wg   = (warp - 4) >> 2;           // 0 or 1
     const int st   = (NST == 2) ? wg : 0;       // stream drained by this warpgroup
     const bool alternate = (NST == 1);
     const int vcta = cta * NST + st, nv = nctas * NST;
     const int q    = warp & 3;                  // TMEM lane quarter this warp may access
-    const int lpix = q * 32 + lane;             // pixel within the strip
-    const bool issuer = ((threadIdx.x - 128) & 127) == 0; // first thread of the warpgroup issues TMA stores
     const float* bias_s = reinterpret_cast<const float*>(sgen + SmemLayout::bias);
     const int CoutG = p.CoutG;
     const bool pool = (p.post_op == POST_POOL);
     const bool relu = p.relu != 0;
     const int ystep = pool ? 2 : 1;
     const int nbuf = p.out_nbuf;
-    const uint32_t out_region = b_region + p.b_bytes + (uint32_t)wg * nbuf * p.out_buf_bytes;
+    const uint32_t wregion = b_region + p.b_bytes + (uint32_t)((wg * 4 + q) * nbuf) * p.out_buf_bytes;
     const uint32_t tfull  = sbase + SmemLayout::tmem_full + 8 * st * kMaxSlots;
     const uint32_t tempty = sbase + SmemLayout::tmem_empty + 8 * st * kMaxSlots;
-    const int spix = pool ? (lpix >> 1) : lpix; // staging row of this thread's pixel
+    const int spix = pool ? (lane >> 1) : lane; // staging row of this thread's pixel inside the warp slice
     const bool writer = !pool || ((lane & 1) == 0);
-    const int bar_a = 1 + 2 * wg, bar_b = 2 + 2 * wg;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)st * (uint32_t)R * CoutG;
     // per-piece constants of this thread's staging row
     uint32_t prow[kMaxOutChunks], pxor[kMaxOutChunks];
@@ -382,6 +397,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
     for (int item = vcta; item < nitems; item += nv)
     {
       const Item it = get_item(p, item);
+      const int xo = (pool ? (it.x0 >> 1) : it.x0) + q * (pool ? 16 : 32);
       uint32_t y_mod = a_mod, y_par = a_par;
       for (int y = it.y0; y <= it.y1; y += ystep, ++rown)
       {
@@ -393,20 +409,19 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
         if (pool) { if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; } }
         if (alternate && (int)(rown & 1) != wg) continue;
 
-        // staging buffer `buf` must have been read out by its previous TMA store
-        if (issuer)
-        {
-          if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-        }
-        named_bar_sync(bar_a, 128);
-
-        mbar_wait(tfull + 8 * slot0, par0, 5);
+        MBAR_WAIT(tfull + 8 * slot0, par0, 5);
         if (pool)
-          mbar_wait(tfull + 8 * slot1, par1, 6);
+          MBAR_WAIT(tfull + 8 * slot1, par1, 6);
         tc_fence_after();
+        // this warp's staging slice `buf` must have been read out by the TMA store that used it last
+        if (lane == 0)
+        {
+          TRACE_WRAP(7, if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>());
+        }
+        __syncwarp();
         const uint32_t t0 = lane_base + slot0 * CoutG;
         const uint32_t t1 = lane_base + slot1 * CoutG;
-        const uint32_t stage_out = out_region + buf * p.out_buf_bytes;
+        const uint32_t stage_out = wregion + buf * p.out_buf_bytes;
 #pragma unroll
         for (int oc = 0; oc < kMaxOutChunks; ++oc)
         {
@@ -456,22 +471,17 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
             }
           }
         }
-        // Release the accumulator slot(s) back to the MMA issuer.
+        // Release the accumulator slot(s) back to the MMA issuer (one arrive per warp), make the
+        // generic-proxy smem writes visible to the TMA engine, then store this warp's pixels.
         tc_fence_before();
+        fence_proxy_async();
         __syncwarp();
         if (lane == 0)
         {
           mbar_arrive(tempty + 8 * slot0);
           if (pool)
             mbar_arrive(tempty + 8 * slot1);
-        }
-        // Make the generic-proxy smem writes visible to the TMA engine, then store the row.
-        fence_proxy_async();
-        named_bar_sync(bar_b, 128);
-        if (issuer)
-        {
           const int yo = pool ? (y >> 1) : y;
-          const int xo = pool ? (it.x0 >> 1) : it.x0;
           for (int oc = 0; oc < p.nout; ++oc)
             tma_store_3d(&p.omap[oc], stage_out + p.out_off[oc], group * CoutG + p.out_c0[oc], xo, yo);
           bulk_commit();
@@ -482,10 +492,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
       a_par ^= (tot / R) & 1;
       a_mod = tot % R;
     }
-    if (issuer) bulk_wait_read<0>();
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
   }
 
   // ---------------------------------------------------------------- teardown
+  TRACE_FLUSH();
   tc_fence_before();
   __syncthreads();
   if (warp == 1)
