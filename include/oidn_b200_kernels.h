@@ -90,7 +90,7 @@ typedef struct oidnb200_conv_info
   int nstrips, nrowchunks, nstreams, out_nbuf;
 } oidnb200_conv_info;
 OIDNB200_API int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info);
-/* Profiling builds (-DOIDN_B200_TRACE) only: device array of 12 x 8 uint64 that receives, per warp
+/* Profiling builds (-DOIDN_B200_TRACE) only: device array of 12 x 16 uint64 that receives, per warp
  * role, the cycles spent blocked at each barrier (tools/probe_conv --trace). No effect otherwise. */
 OIDNB200_API int oidnb200_conv_set_trace(oidnb200_conv* conv, void* trace_counters);
 

@@ -25,6 +25,25 @@ constexpr int kTmemCols    = 512;
 constexpr int kMaxSlots    = 16;
 constexpr int kSmemBudget  = 232448; // 227 KB opt-in dynamic shared memory per CTA
 
+// Output-channel pieces of a group of nb*16 channels: 64-channel pieces, then 32, then 16 (the TMA
+// store box / swizzle widths). Shared by the planner (tensor maps) and the kernel (staging layout).
+__host__ __device__ constexpr int out_piece_count(int nb) { return nb / 4 + ((nb >> 1) & 1) + (nb & 1); }
+__host__ __device__ constexpr int out_piece_cc(int nb, int i)
+{
+  return i < nb / 4 ? 64 : ((i == nb / 4 && (nb & 2)) ? 32 : 16);
+}
+__host__ __device__ constexpr int out_piece_c0(int nb, int i)
+{
+  return i <= nb / 4 ? i * 64 : (nb / 4) * 64 + 32;
+}
+// byte offset of piece i inside one staging slice of `rows` pixels (every piece 1024-aligned)
+__host__ __device__ constexpr uint32_t out_piece_off(int nb, int i, int rows)
+{
+  uint32_t off = 0;
+  for (int k = 0; k < i; ++k) off += ((uint32_t)(rows * out_piece_cc(nb, k) * 2) + 1023u) / 1024u * 1024u;
+  return off;
+}
+
 enum PostOp : int { POST_NONE = 0, POST_POOL = 1, POST_UPSAMPLE = 2 /* SIMT witness only */ };
 
 struct ConvKernelParams
@@ -39,6 +58,12 @@ struct ConvKernelParams
   int      chunk_up[kMaxChunks];    // 1: source stored at half resolution, read through the 4D dup map
   uint32_t chunk_boff[kMaxChunks];  // byte offset of the chunk's kw=0 weight block in the B region
   uint32_t chunk_bblk[kMaxChunks];  // bytes of one kw block (3*CoutG rows)
+  // the MMA issuer's per-chunk constants (descriptor arithmetic is in 16-byte units)
+  uint32_t chunk_nk[kMaxChunks];    // 16-channel k-steps in the chunk (1, 2 or 4)
+  uint32_t chunk_hi[kMaxChunks];    // high word of the chunk's UMMA shared-memory descriptors
+  uint32_t chunk_a16[kMaxChunks];   // start of the strip inside a stage: one pixel in for an upsampled source
+  uint32_t chunk_b16[kMaxChunks];   // chunk_boff / 16
+  uint32_t chunk_bblk16[kMaxChunks]; // chunk_bblk / 16
   int      H, W;                    // conv resolution (= resolution of the unpooled output)
   int      CoutG, ngroups, CoutPad; // output channels per CTA group / groups / padded total
   int      nstreams;                // 1 or 2 independent row streams per CTA
@@ -56,7 +81,7 @@ struct ConvKernelParams
   int      out_nbuf;                // 1 or 2 staging slices per epilogue warp (8 warps)
   int      relu, post_op;
   const float* bias;                // fp32 [CoutAlloc]
-  unsigned long long* trace;        // [12 warps][8 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
+  unsigned long long* trace;        // [12 warps][16 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
 };
 
 } // namespace oidnb200

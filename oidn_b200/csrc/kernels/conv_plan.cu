@@ -208,24 +208,32 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
     off = align_up(off, 1024);
     kp.chunk_boff[c] = off;
     kp.chunk_bblk[c] = 3u * CoutG * kp.chunk_cc[c] * 2u;
+    {
+      const uint32_t rowb = (uint32_t)kp.chunk_cc[c] * 2u;   // bytes of one staged pixel / weight row
+      const uint32_t layout = rowb == 128 ? 2u : (rowb == 64 ? 4u : 6u); // 128B / 64B / 32B swizzle
+      kp.chunk_nk[c] = (uint32_t)kp.chunk_cc[c] / 16u;
+      // sm_100 descriptor high word: SBO = 8 rows (bits 32..45), version 1 (bit 46), swizzle (bits 61..63)
+      kp.chunk_hi[c] = (((8u * rowb) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+      kp.chunk_a16[c] = kp.chunk_up[c] ? rowb >> 4 : 0u;
+      kp.chunk_b16[c] = off >> 4;
+      kp.chunk_bblk16[c] = kp.chunk_bblk[c] >> 4;
+    }
     off += 3u * kp.chunk_bblk[c];
   }
   const uint32_t bbytes = align_up(off, 1024);
   kp.b_bytes = bbytes;
   kp.w_bytes = 9u * CoutG * pl.CinTot * 2u;
 
-  // output pieces
-  kp.nout = 0;
+  // output pieces (same constexpr decomposition the kernel's epilogue is specialised on)
+  const int NB = CoutG / 16;
+  kp.nout = out_piece_count(NB);
   uint32_t ooff = 0;
-  for (int c0 = 0, rem = CoutG; rem > 0;)
+  for (int i = 0; i < kp.nout; ++i)
   {
-    const int cc = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
-    ooff = align_up(ooff, 1024);
-    kp.out_c0[kp.nout] = c0;
-    kp.out_cc[kp.nout] = cc;
-    kp.out_off[kp.nout] = ooff;
-    ooff += out_rows * cc * 2u;
-    c0 += cc; rem -= cc; kp.nout++;
+    kp.out_c0[i] = out_piece_c0(NB, i);
+    kp.out_cc[i] = out_piece_cc(NB, i);
+    kp.out_off[i] = out_piece_off(NB, i, (int)out_rows);
+    ooff = kp.out_off[i] + out_rows * kp.out_cc[i] * 2u;
   }
   kp.out_buf_bytes = align_up(ooff, 1024);
 

@@ -41,12 +41,20 @@ using namespace ptx;
 // Optional wait-time tracing (build with -DOIDN_B200_TRACE, tools/probe_conv --trace): every role
 // accumulates the cycles it spends blocked at each barrier; lane 0 adds them to p.trace[warp][tag].
 #ifdef OIDN_B200_TRACE
-#define TRACE_DECL long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_start = clock64();
+#define TRACE_DECL long long tr[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_start = clock64(); long long tr_t = 0;
 #define MBAR_WAIT(bar, par, tag) do { const long long t0_ = clock64(); mbar_wait(bar, par, tag); tr[tag] += clock64() - t0_; } while (0)
 #define TRACE_WRAP(tag, stmt) do { const long long t0_ = clock64(); stmt; tr[tag] += clock64() - t0_; } while (0)
 #define TRACE_FLUSH() do { if (p.trace && lane == 0) { tr[0] = clock64() - tr_start; \
-  for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&p.trace[warp * 8 + i_], (unsigned long long)tr[i_]); } } while (0)
+  for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&p.trace[warp * 16 + i_], (unsigned long long)tr[i_]); } } while (0)
+#define TRACE_ARGS , tr, tr_t
+#define TRACE_PARAMS , long long* tr, long long& tr_t
+#define TRACE_BEGIN() do { tr_t = clock64(); } while (0)
+#define TRACE_END(tag) do { const long long t1_ = clock64(); tr[tag] += t1_ - tr_t; tr_t = t1_; } while (0)
 #else
+#define TRACE_ARGS
+#define TRACE_PARAMS
+#define TRACE_BEGIN()
+#define TRACE_END(tag)
 #define TRACE_DECL
 #define MBAR_WAIT(bar, par, tag) mbar_wait(bar, par, tag)
 #define TRACE_WRAP(tag, stmt) stmt
@@ -91,20 +99,29 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b)
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ uint32_t relu_half2(uint32_t x)
+// {lo, hi} -> packed fp16 pair with max(x, 0) folded into the conversion
+__device__ __forceinline__ uint32_t pack_half2_relu(float lo, float hi)
 {
   uint32_t r;
-  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(0u));
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t max_half2(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
 
 // All tcgen05.mma of one staged (row, K-chunk): 3 horizontal taps x NK k-steps x (1 or 2) runs,
 // fully unrolled so that each MMA costs two descriptor adds plus the issue.
 template <int NK, bool TWO>
-__device__ __forceinline__ void issue_chunk(uint32_t hi, uint32_t a_lo, uint32_t row16, uint32_t b_lo,
+__device__ __forceinline__ void issue_chunk(uint32_t hi, uint32_t a_lo, uint32_t b_lo,
                                             uint32_t bblk16, uint32_t d0, uint32_t idesc0, uint32_t rb0,
                                             uint32_t d1, uint32_t idesc1, uint32_t rb1, bool skip_first)
 {
+  constexpr uint32_t row16 = NK * 2; // bytes of one staged pixel / 16
 #pragma unroll
   for (int kw = 0; kw < 3; ++kw)
   {
@@ -120,6 +137,214 @@ __device__ __forceinline__ void issue_chunk(uint32_t hi, uint32_t a_lo, uint32_t
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue
+// ------------------------------------------------------------------------------------------------
+struct EpiCtx
+{
+  uint32_t sbase, tmem_base, b_region;
+  uint8_t* sgen;
+  int warp, lane, group, cta, nctas;
+};
+
+// Bias add (fp32, packed pairs) + fp16 rounding (+ReLU) of W accumulator columns; W = 16 or 32.
+template <int W>
+__device__ __forceinline__ void bias_cvt(const uint32_t (&v)[W], const float2* bias2, bool relu, uint32_t (&h)[W / 2])
+{
+#pragma unroll
+  for (int i = 0; i < W / 2; ++i)
+  {
+    const float2 s = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bias2[i]);
+    h[i] = relu ? pack_half2_relu(s.x, s.y) : pack_half2(s.x, s.y);
+  }
+}
+
+// Two warpgroups of 128 threads = the 128 TMEM lanes (pixels) of an accumulator. With two streams,
+// warpgroup g drains every row of stream g; with one stream the two warpgroups drain alternate
+// rows (row pairs when pooling). Every WARP is its own store pipeline: it owns the 32 pixels of its
+// TMEM lane quarter, stages them in its own (double-buffered) swizzled smem slice and issues its
+// own TMA store, so a row costs no CTA-level barrier:
+//   TMEM -> registers -> (max of the two rows) -> +bias (fp32) -> fp16 (+ReLU) -> (max of the pixel
+//   pair) -> smem slice -> TMA store.
+// max commutes with the monotonic "+bias, round" so pooling after rounding is bit-identical to
+// pooling the rounded full-resolution tensor (what the reference's separate pool pass does).
+template <int NB, bool POOL>
+__device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx& ec TRACE_PARAMS)
+{
+  constexpr int CoutG = NB * 16;
+  constexpr int NP    = out_piece_count(NB);
+  constexpr int PROWS = POOL ? 16 : 32;       // staging rows (pixels) of one warp
+  const int warp = ec.warp, lane = ec.lane;
+  const int NST  = p.nstreams;
+  const int R    = p.R;
+  const int wg   = (warp - 4) >> 2;           // 0 or 1
+  const int st   = (NST == 2) ? wg : 0;       // stream drained by this warpgroup
+  const bool alternate = (NST == 1);
+  const int vcta = ec.cta * NST + st, nv = ec.nctas * NST;
+  const int nitems = p.nstrips * p.nrowchunks;
+  const int q    = warp & 3;                  // TMEM lane quarter this warp may access
+  const bool relu = p.relu != 0;
+  const int nbuf = p.out_nbuf;
+  const uint32_t wregion = ec.b_region + p.b_bytes + (uint32_t)((wg * 4 + q) * nbuf) * p.out_buf_bytes;
+  const uint32_t tfull  = ec.sbase + SmemLayout::tmem_full + 8 * st * kMaxSlots;
+  const uint32_t tempty = ec.sbase + SmemLayout::tmem_empty + 8 * st * kMaxSlots;
+  const int spix = POOL ? (lane >> 1) : lane; // staging row of this thread's pixel inside the warp slice
+  const bool writer = !POOL || ((lane & 1) == 0);
+  const uint32_t lane_base = ec.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)st * (uint32_t)R * CoutG;
+  const float2* bias_s = reinterpret_cast<const float2*>(ec.sgen + SmemLayout::bias);
+
+  // this thread's staging row inside each piece and its swizzle term (16-B chunk ^= 128-B line mod chunks)
+  uint32_t prow[NP], pxor[NP];
+#pragma unroll
+  for (int oc = 0; oc < NP; ++oc)
+  {
+    constexpr int dummy = 0; (void)dummy;
+    const uint32_t rowb = (uint32_t)out_piece_cc(NB, oc) * 2u;
+    const uint32_t off = (uint32_t)spix * rowb;
+    prow[oc] = out_piece_off(NB, oc, PROWS) + off;
+    pxor[oc] = ((off >> 7) & ((rowb >> 4) - 1u)) << 4;
+  }
+  // narrow groups keep their bias in registers
+  constexpr bool kBiasRegs = (NB <= 2);
+  float2 breg[kBiasRegs ? NB * 8 : 1];
+  if (kBiasRegs)
+  {
+#pragma unroll
+    for (int i = 0; i < NB * 8; ++i) breg[i] = bias_s[i];
+  }
+
+  uint32_t a_mod = 0, a_par = 0;
+  uint32_t buf = 0, rown = 0;
+  for (int item = vcta; item < nitems; item += nv)
+  {
+    const Item it = get_item(p, item);
+    const int xo = (POOL ? (it.x0 >> 1) : it.x0) + q * PROWS;
+    uint32_t y_mod = a_mod, y_par = a_par;
+    for (int y = it.y0; y <= it.y1; y += (POOL ? 2 : 1), ++rown)
+    {
+      const uint32_t slot0 = (R - 1) - y_mod;
+      const uint32_t par0 = y_par;
+      if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; }
+      uint32_t slot1 = 0, par1 = 0;
+      if (POOL)
+      {
+        slot1 = (R - 1) - y_mod; par1 = y_par;
+        if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; }
+      }
+      if (alternate && (int)(rown & 1) != wg) continue;
+
+      MBAR_WAIT(tfull + 8 * slot0, par0, 5);
+      if (POOL)
+        MBAR_WAIT(tfull + 8 * slot1, par1, 6);
+      tc_fence_after();
+      // this warp's staging slice `buf` must have been read out by the TMA store that used it last
+      if (lane == 0)
+      {
+        TRACE_WRAP(7, if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>());
+      }
+      __syncwarp();
+      TRACE_BEGIN();
+      const uint32_t t0 = lane_base + slot0 * CoutG;
+      const uint32_t t1 = lane_base + slot1 * CoutG;
+      const uint32_t stage_out = wregion + buf * p.out_buf_bytes;
+#pragma unroll
+      for (int oc = 0; oc < NP; ++oc)
+      {
+        constexpr int dummy2 = 0; (void)dummy2;
+        const int c0 = out_piece_c0(NB, oc), ccw = out_piece_cc(NB, oc);
+        const uint32_t rowaddr = stage_out + prow[oc];
+        const uint32_t xr = pxor[oc];
+#pragma unroll
+        for (int j = 0; j < ccw; j += 32)
+        {
+          if (ccw - j >= 32)
+          {
+            uint32_t v[32], h[16];
+            tmem_ld32(t0 + c0 + j, v);
+            if (POOL)
+            {
+              uint32_t w[32];
+              tmem_ld32(t1 + c0 + j, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), __uint_as_float(w[i])));
+            }
+            else
+              tmem_ld_wait();
+            TRACE_END(8);
+            bias_cvt<32>(v, kBiasRegs ? &breg[(c0 + j) / 2] : bias_s + (c0 + j) / 2, relu, h);
+            if (POOL)
+            {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) h[i] = max_half2(h[i], __shfl_xor_sync(0xffffffffu, h[i], 1));
+            }
+            if (writer)
+            {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                st_shared_v4(rowaddr + (((uint32_t)(j * 2 + k * 16)) ^ xr), h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+            }
+            TRACE_END(9);
+          }
+          else
+          {
+            uint32_t v[16], h[8];
+            tmem_ld16(t0 + c0 + j, v);
+            if (POOL)
+            {
+              uint32_t w[16];
+              tmem_ld16(t1 + c0 + j, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), __uint_as_float(w[i])));
+            }
+            else
+              tmem_ld_wait();
+            TRACE_END(8);
+            bias_cvt<16>(v, kBiasRegs ? &breg[(c0 + j) / 2] : bias_s + (c0 + j) / 2, relu, h);
+            if (POOL)
+            {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[i] = max_half2(h[i], __shfl_xor_sync(0xffffffffu, h[i], 1));
+            }
+            if (writer)
+            {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                st_shared_v4(rowaddr + (((uint32_t)(j * 2 + k * 16)) ^ xr), h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+            }
+            TRACE_END(9);
+          }
+        }
+      }
+      // Release the accumulator slot(s) back to the MMA issuer (one arrive per warp), make the
+      // generic-proxy smem writes visible to the TMA engine, then store this warp's pixels.
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      TRACE_END(10);
+      if (lane == 0)
+      {
+        mbar_arrive(tempty + 8 * slot0);
+        if (POOL)
+          mbar_arrive(tempty + 8 * slot1);
+        const int yo = POOL ? (y >> 1) : y;
+#pragma unroll
+        for (int oc = 0; oc < NP; ++oc)
+          tma_store_3d(&p.omap[oc], stage_out + out_piece_off(NB, oc, PROWS), ec.group * CoutG + out_piece_c0(NB, oc), xo, yo);
+        bulk_commit();
+      }
+      TRACE_END(11);
+      if (++buf == (uint32_t)nbuf) buf = 0;
+    }
+    const uint32_t tot = a_mod + (uint32_t)(it.y1 - it.y0 + 1);
+    a_par ^= (tot / R) & 1;
+    a_mod = tot % R;
+  }
+  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
+}
+
 } // namespace
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -129,7 +354,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler can then prove it warp-uniform and keep the role
+  // loops' state in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   TRACE_DECL
 
@@ -244,15 +471,21 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
       else
       {
         // One lane issues every tcgen05.mma of the stream, so this loop must cost only a handful
-        // of instructions per MMA: descriptors are (constant high word | running low word),
-        // ring/slot arithmetic is hoisted to once per input row, there are at most two runs per
-        // row, and the per-chunk issue sequence is fully unrolled (issue_chunk).
+        // of instructions per MMA and per row: everything below is warp-uniform (uniform
+        // registers), descriptors are (per-chunk constant high word | running low word), the
+        // per-chunk constants come precomputed from the planner, a row is at most two runs of
+        // accumulators contiguous in TMEM, and the per-chunk issue sequence is fully unrolled.
         const uint32_t tfull  = sbase + SmemLayout::tmem_full + 8 * st * kMaxSlots;
         const uint32_t tempty = sbase + SmemLayout::tmem_empty + 8 * st * kMaxSlots;
         const uint32_t CoutG = p.CoutG;
         const uint32_t tbase = tmem_base + (uint32_t)st * (uint32_t)R * CoutG; // this stream's columns
         const uint32_t max_run = min(3u, 256u / CoutG);
         const uint32_t idesc1 = umma_idesc_f16(CoutG);
+        const uint32_t sbase16 = (sbase & 0x3FFFFu) >> 4;
+        const uint32_t ring16  = sbase16 + ((SmemLayout::a_ring + (uint32_t)(st * NS) * stage_bytes) >> 4);
+        const uint32_t stage16 = stage_bytes >> 4;
+        const uint32_t breg16  = sbase16 + ((SmemLayout::a_ring + (uint32_t)(NST * NS) * stage_bytes) >> 4);
+        const int nchunks = p.nchunks;
         MBAR_WAIT(sbase + SmemLayout::w_full, 0, 2);
         tc_fence_after();
         uint32_t stage = 0, sphase = 0;       // A ring position / parity
@@ -273,43 +506,34 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
               MBAR_WAIT(tempty + 8 * ((R - 1) - top_mod), top_par ^ 1, 3);
               tc_fence_after();
             }
-            // Split kh_lo..kh_hi into (at most two) runs contiguous in TMEM (ring wrap), N <= 256.
-            uint32_t d0 = 0, n0 = 0, brow0 = 0, d1 = 0, n1 = 0, brow1 = 0;
-            for (int kh = kh_lo; kh <= kh_hi; ++kh)
-            {
-              int m = (int)top_mod - kh;
-              if (m < 0) m += R;
-              const uint32_t slot = (R - 1) - m;
-              if (n0 == 0)
-              {
-                d0 = tbase + slot * CoutG; brow0 = kh * CoutG; n0 = 1;
-              }
-              else if (n1 == 0 && slot != 0 && n0 < max_run)
-                n0++;
-              else if (n1 == 0)
-              {
-                d1 = tbase + slot * CoutG; brow1 = kh * CoutG; n1 = 1;
-              }
-              else
-                n1++;
-            }
+            // Accumulators of kh_lo..kh_hi sit in consecutive ring slots S, S+1, .. (mod R): at most
+            // two runs contiguous in TMEM (ring wrap, N <= 256).
+            int m = (int)top_mod - kh_lo;
+            if (m < 0) m += R;
+            const uint32_t S  = (uint32_t)((R - 1) - m);
+            const uint32_t n  = (uint32_t)(kh_hi - kh_lo + 1);
+            const uint32_t n0 = min(min(n, max_run), (uint32_t)R - S);
+            const uint32_t n1 = n - n0;
+            uint32_t S1 = S + n0;
+            if (S1 >= (uint32_t)R) S1 -= R;
+            const uint32_t d0 = tbase + S * CoutG, d1 = tbase + S1 * CoutG;
+            const uint32_t brow0 = (uint32_t)kh_lo * CoutG, brow1 = brow0 + n0 * CoutG; // weight rows
             const uint32_t idesc_r0 = umma_idesc_f16(n0 * CoutG);
             const uint32_t idesc_r1 = umma_idesc_f16(n1 * CoutG);
 
-            for (int c = 0; c < p.nchunks; ++c)
+            for (int c = 0; c < nchunks; ++c)
             {
-              const uint32_t cc     = p.chunk_cc[c];
-              const uint32_t row16  = cc >> 3;                      // row bytes / 16
-              const uint32_t hi     = (uint32_t)(umma_desc(0, cc * 2, 0) >> 32); // SBO, version, swizzle
-              const uint32_t a_base = a_ring + stage * stage_bytes
-                                      + (p.chunk_up[c] ? cc * 2 : 0); // upsampled rows start at x0-2
-              const uint32_t a_lo   = (a_base & 0x3FFFFu) >> 4;
-              const uint32_t b_lo   = ((b_region + p.chunk_boff[c]) & 0x3FFFFu) >> 4;
-              const uint32_t bblk16 = p.chunk_bblk[c] >> 4;
+              const uint32_t nk     = p.chunk_nk[c];                 // 16-channel k-steps: 1, 2 or 4
+              const uint32_t row16  = nk * 2;                        // row bytes / 16
+              const uint32_t hi     = p.chunk_hi[c];                 // SBO, version, swizzle
+              const uint32_t a_lo   = ring16 + stage * stage16 + p.chunk_a16[c]; // upsampled rows start at x0-2
+              const uint32_t b_lo   = breg16 + p.chunk_b16[c];
+              const uint32_t bblk16 = p.chunk_bblk16[c];
               const uint32_t rb0 = brow0 * row16, rb1 = brow1 * row16;
               const bool first = fresh && c == 0;
               MBAR_WAIT(full_a + 8 * stage, sphase, 4);
               tc_fence_after();
+              TRACE_BEGIN();
               if (leader)
               {
                 if (first)
@@ -324,27 +548,28 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
                 }
                 if (n1)
                 {
-                  if (cc == 64)      issue_chunk<4, true>(hi, a_lo, row16, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else if (cc == 32) issue_chunk<2, true>(hi, a_lo, row16, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else               issue_chunk<1, true>(hi, a_lo, row16, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  if (nk == 4)      issue_chunk<4, true>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  else if (nk == 2) issue_chunk<2, true>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  else              issue_chunk<1, true>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
                 }
                 else
                 {
-                  if (cc == 64)      issue_chunk<4, false>(hi, a_lo, row16, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else if (cc == 32) issue_chunk<2, false>(hi, a_lo, row16, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else               issue_chunk<1, false>(hi, a_lo, row16, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  if (nk == 4)      issue_chunk<4, false>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  else if (nk == 2) issue_chunk<2, false>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  else              issue_chunk<1, false>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
                 }
                 umma_commit(empty_a + 8 * stage); // stage reusable once these MMAs retire
               }
+              TRACE_END(8);
               if (++stage == (uint32_t)NS) { stage = 0; sphase ^= 1; }
             }
             // Output row r-1 has now received kh=0,1,2.
             if (r - 1 >= it.y0 && r - 1 <= it.y1)
             {
-              int m = (int)top_mod - 2;
-              if (m < 0) m += R;
+              int m2 = (int)top_mod - 2;
+              if (m2 < 0) m2 += R;
               if (leader)
-                umma_commit(tfull + 8 * ((R - 1) - m));
+                umma_commit(tfull + 8 * ((R - 1) - m2));
             }
             if (++top_mod == (uint32_t)R) { top_mod = 0; top_par ^= 1; }
           }
@@ -359,141 +584,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   // ---------------------------------------------------------------- epilogue
   else
   {
-    // Two warpgroups of 128 threads = the 128 TMEM lanes (pixels) of an accumulator. With two
-    // streams, warpgroup g drains every row of stream g; with one stream the two warpgroups drain
-    // alternate rows (row pairs when pooling). Every WARP is its own store pipeline: it owns the 32
-    // pixels of its TMEM lane quarter, stages them in its own (double-buffered) swizzled smem
-    // slice and issues its own TMA store, so a row costs no CTA-level barrier:
-    // TMEM -> registers -> +bias (fp32) -> fp16 -> ReLU -> (2x2 max) -> smem slice -> TMA store.
-    const int wg   = (warp - 4) >> 2;           // 0 or 1
-    const int st   = (NST == 2) ? wg : 0;       // stream drained by this warpgroup
-    const bool alternate = (NST == 1);
-    const int vcta = cta * NST + st, nv = nctas * NST;
-    const int q    = warp & 3;                  // TMEM lane quarter this warp may access
-    const float* bias_s = reinterpret_cast<const float*>(sgen + SmemLayout::bias);
-    const int CoutG = p.CoutG;
-    const bool pool = (p.post_op == POST_POOL);
-    const bool relu = p.relu != 0;
-    const int ystep = pool ? 2 : 1;
-    const int nbuf = p.out_nbuf;
-    const uint32_t wregion = b_region + p.b_bytes + (uint32_t)((wg * 4 + q) * nbuf) * p.out_buf_bytes;
-    const uint32_t tfull  = sbase + SmemLayout::tmem_full + 8 * st * kMaxSlots;
-    const uint32_t tempty = sbase + SmemLayout::tmem_empty + 8 * st * kMaxSlots;
-    const int spix = pool ? (lane >> 1) : lane; // staging row of this thread's pixel inside the warp slice
-    const bool writer = !pool || ((lane & 1) == 0);
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)st * (uint32_t)R * CoutG;
-    // per-piece constants of this thread's staging row
-    uint32_t prow[kMaxOutChunks], pxor[kMaxOutChunks];
-#pragma unroll
-    for (int oc = 0; oc < kMaxOutChunks; ++oc)
+    // Specialised per (CoutG / 16, pool): the row loop is the instruction-bound part of the narrow,
+    // HBM-bound layers (one warp retires a 32-pixel row segment in ~80 instructions).
+    EpiCtx ec;
+    ec.sbase = sbase; ec.tmem_base = tmem_base; ec.b_region = b_region; ec.sgen = sgen;
+    ec.warp = warp; ec.lane = lane; ec.group = group; ec.cta = cta; ec.nctas = nctas;
+    switch ((p.CoutG >> 4) * 2 + (p.post_op == POST_POOL ? 1 : 0))
     {
-      const uint32_t rowb = (uint32_t)p.out_cc[oc] * 2u;
-      const uint32_t off = (uint32_t)spix * rowb;
-      prow[oc] = p.out_off[oc] + off;
-      pxor[oc] = ((off >> 7) & ((rowb >> 4) - 1u)) << 4;  // swizzle: chunk ^= (128-B line index mod chunks)
+#define EPI_CASE(NB) case (NB) * 2: epilogue<NB, false>(p, ec TRACE_ARGS); break; case (NB) * 2 + 1: epilogue<NB, true>(p, ec TRACE_ARGS); break;
+      EPI_CASE(1) EPI_CASE(2) EPI_CASE(3) EPI_CASE(4) EPI_CASE(5) EPI_CASE(6) EPI_CASE(7) EPI_CASE(8)
+#undef EPI_CASE
+      default: break;
     }
-    uint32_t a_mod = 0, a_par = 0;
-    uint32_t buf = 0, rown = 0;
-    for (int item = vcta; item < nitems; item += nv)
-    {
-      const Item it = get_item(p, item);
-      const int xo = (pool ? (it.x0 >> 1) : it.x0) + q * (pool ? 16 : 32);
-      uint32_t y_mod = a_mod, y_par = a_par;
-      for (int y = it.y0; y <= it.y1; y += ystep, ++rown)
-      {
-        const uint32_t slot0 = (R - 1) - y_mod;
-        const uint32_t par0 = y_par;
-        if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; }
-        const uint32_t slot1 = (R - 1) - y_mod;
-        const uint32_t par1 = y_par;
-        if (pool) { if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; } }
-        if (alternate && (int)(rown & 1) != wg) continue;
-
-        MBAR_WAIT(tfull + 8 * slot0, par0, 5);
-        if (pool)
-          MBAR_WAIT(tfull + 8 * slot1, par1, 6);
-        tc_fence_after();
-        // this warp's staging slice `buf` must have been read out by the TMA store that used it last
-        if (lane == 0)
-        {
-          TRACE_WRAP(7, if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>());
-        }
-        __syncwarp();
-        const uint32_t t0 = lane_base + slot0 * CoutG;
-        const uint32_t t1 = lane_base + slot1 * CoutG;
-        const uint32_t stage_out = wregion + buf * p.out_buf_bytes;
-#pragma unroll
-        for (int oc = 0; oc < kMaxOutChunks; ++oc)
-        {
-          if (oc < p.nout)
-          {
-            const int c0 = p.out_c0[oc], ccw = p.out_cc[oc];
-            const uint32_t rowaddr = stage_out + prow[oc];
-            const uint32_t xr = pxor[oc];
-            for (int j = 0; j < ccw; j += 16)
-            {
-              uint32_t v[16];
-              tmem_ld16(t0 + c0 + j, v);
-              if (pool)
-              {
-                uint32_t w[16];
-                tmem_ld16(t1 + c0 + j, w);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                {
-                  const float m = fmaxf(__uint_as_float(v[i]), __uint_as_float(w[i]));
-                  v[i] = __float_as_uint(fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1)));
-                }
-              }
-              else
-                tmem_ld_wait();
-              const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0 + j);
-              uint32_t h[8];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-              {
-                const float4 bb = b4[i];
-                h[2 * i]     = pack_half2(__uint_as_float(v[4 * i]) + bb.x, __uint_as_float(v[4 * i + 1]) + bb.y);
-                h[2 * i + 1] = pack_half2(__uint_as_float(v[4 * i + 2]) + bb.z, __uint_as_float(v[4 * i + 3]) + bb.w);
-              }
-              if (relu)
-              {
-                // max(x, 0) commutes with the monotonic fp32->fp16 rounding, so it runs on packed halves
-#pragma unroll
-                for (int i = 0; i < 8; ++i) h[i] = relu_half2(h[i]);
-              }
-              if (writer)
-              {
-                st_shared_v4(rowaddr + (((uint32_t)j * 2u) ^ xr), h[0], h[1], h[2], h[3]);
-                st_shared_v4(rowaddr + (((uint32_t)j * 2u + 16u) ^ xr), h[4], h[5], h[6], h[7]);
-              }
-            }
-          }
-        }
-        // Release the accumulator slot(s) back to the MMA issuer (one arrive per warp), make the
-        // generic-proxy smem writes visible to the TMA engine, then store this warp's pixels.
-        tc_fence_before();
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0)
-        {
-          mbar_arrive(tempty + 8 * slot0);
-          if (pool)
-            mbar_arrive(tempty + 8 * slot1);
-          const int yo = pool ? (y >> 1) : y;
-          for (int oc = 0; oc < p.nout; ++oc)
-            tma_store_3d(&p.omap[oc], stage_out + p.out_off[oc], group * CoutG + p.out_c0[oc], xo, yo);
-          bulk_commit();
-        }
-        if (++buf == (uint32_t)nbuf) buf = 0;
-      }
-      const uint32_t tot = a_mod + (uint32_t)(it.y1 - it.y0 + 1);
-      a_par ^= (tot / R) & 1;
-      a_mod = tot % R;
-    }
-    if (lane == 0) bulk_wait_read<0>();
-    __syncwarp();
   }
 
   // ---------------------------------------------------------------- teardown

@@ -91,17 +91,17 @@ int main(int argc, char** argv)
 
   if (iters > 0 && !bad && getenv("PROBE_TRACE"))
   {
-    unsigned long long* dtr; CK(cudaMalloc(&dtr, 96 * 8)); CK(cudaMemset(dtr, 0, 96 * 8));
+    unsigned long long* dtr; CK(cudaMalloc(&dtr, 192 * 8)); CK(cudaMemset(dtr, 0, 192 * 8));
     oidnb200_conv_set_trace(conv, dtr);
     oidnb200_conv_bind(conv, d1, d2, dw, db, dout);
     oidnb200_conv_launch(conv, 0); CK(cudaDeviceSynchronize());
-    unsigned long long tr[96]; CK(cudaMemcpy(tr, dtr, sizeof(tr), cudaMemcpyDeviceToHost));
+    unsigned long long tr[192]; CK(cudaMemcpy(tr, dtr, sizeof(tr), cudaMemcpyDeviceToHost));
     const char* roles[12] = {"TMA0", "MMA0", "TMA1", "MMA1", "EPI0.0", "EPI0.1", "EPI0.2", "EPI0.3", "EPI1.0", "EPI1.1", "EPI1.2", "EPI1.3"};
-    printf("TRACE (cycles summed over %d CTAs; tags: 1 A-empty 2 weights 3 tmem-empty 4 A-full 5 tmem-full 6 tmem-full(pool) 7 store-read)\n", info.grid);
+    printf("TRACE (cycles summed over %d CTAs; tags: 1 A-empty 2 weights 3 tmem-empty 4 A-full 5 tmem-full 6 tmem-full(pool) 7 store-read; MMA 8 issue; EPI 8 tmem-ld 9 math+sts 10 fences 11 arrive+store)\n", info.grid);
     for (int w = 0; w < 12; ++w)
     {
-      printf("  %-7s total %10.0f/CTA |", roles[w], (double)tr[w * 8] / info.grid);
-      for (int t = 1; t < 8; ++t) if (tr[w * 8 + t]) printf(" wait%d %5.1f%%", t, 100.0 * tr[w * 8 + t] / (double)tr[w * 8]);
+      printf("  %-7s total %10.0f/CTA |", roles[w], (double)tr[w * 16] / info.grid);
+      for (int t = 1; t < 16; ++t) if (tr[w * 16 + t]) printf(" t%d %5.1f%%", t, 100.0 * tr[w * 16 + t] / (double)tr[w * 16]);
       printf("\n");
     }
     oidnb200_conv_set_trace(conv, nullptr);
