@@ -70,6 +70,7 @@ struct ConvKernelParams
   int      R;                       // TMEM accumulator ring slots per stream (nstreams*R*CoutG <= 512)
   int      RC, nstrips, nrowchunks; // rows per work item, strips across W, row chunks down H
   int      nstages;                 // A pipeline stages per stream
+  int      prefetch_rows;           // > 0: the TMA producer prefetches input rows this far ahead into L2
   uint32_t stage_bytes;             // bytes of one A stage: 132 px x the widest K chunk, 1024-aligned
   uint32_t w_bytes;                 // total weight bytes TMA-loaded per CTA
   uint32_t b_bytes;                 // size of the resident weight region (1024-aligned blocks)

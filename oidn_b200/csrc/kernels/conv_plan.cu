@@ -6,6 +6,7 @@
 #include "../../../include/oidn_b200_kernels.h"
 #include <cuda_fp16.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -260,6 +261,12 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
     kp.out_nbuf = 1; kp.nstreams = ns1; kp.nstages = st1;
   }
   kp.R = std::min(kMaxSlots, (kTmemCols / kp.nstreams) / CoutG);
+  // A ring that cannot hold even one input row (all K chunks) does not hide HBM latency: the TMA
+  // producer then pulls the rows ahead into L2 first. Measured (profiles/r01_prefetch_ab.log):
+  // dec_conv2a 0.272 -> 0.250 ms, dec_conv3a 0.144 -> 0.139 ms; deeper rings lose ~1 %.
+  // OIDN_B200_PREFETCH overrides the choice (hardware probing only).
+  kp.prefetch_rows = (kp.nstages < n) ? 2 : 0;
+  if (const char* e = getenv("OIDN_B200_PREFETCH")) kp.prefetch_rows = atoi(e);
   pl.smem = 1024 + kSmemHeader + (size_t)kp.nstreams * kp.nstages * stage_bytes + bbytes +
             (size_t)kEpiWarps * kp.out_nbuf * kp.out_buf_bytes;
 

@@ -408,6 +408,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();   // this CTA's resources are the gate for the next grid's CTAs anyway
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + SmemLayout::tmem_ptr);
 
   // Both single-issuer roles keep warp-uniform control flow (all 32 lanes walk the loops, one
@@ -434,12 +435,37 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
               tma_load_4d(b_region + p.chunk_boff[c] + kw * p.chunk_bblk[c], &p.wmap[c],
                           sbase + SmemLayout::w_full, p.chunk_wc0[c], group * p.CoutG, 0, kw);
         }
+        // The launch may overlap the tail of the previous kernel in the stream (programmatic
+        // dependent launch): everything above touched only weights; activations written by that
+        // kernel are first read here, and this kernel's stores are ordered after these loads.
+        pdl_wait();
         uint32_t s = 0, ph = 0;
+        const int PF = p.prefetch_rows;
         for (int item = vcta; item < nitems; item += nv)
         {
           const Item it = get_item(p, item);
+          // Shallow rings (wide layers: the resident weights take most of the shared memory) cannot
+          // cover HBM latency with stages in flight, so the rows ahead are pulled into L2 first.
+          if (PF > 0 && leader)
+          {
+            for (int r = it.y0 - 1; r < min(it.y0 - 1 + PF, it.y1 + 2); ++r)
+              for (int c = 0; c < p.nchunks; ++c)
+              {
+                if (p.chunk_up[c]) tma_prefetch_4d(&p.amap[c], p.chunk_c0[c], 0, it.x0 / 2 - 1, r >> 1);
+                else               tma_prefetch_3d(&p.amap[c], p.chunk_c0[c], it.x0 - 1, r);
+              }
+          }
           for (int r = it.y0 - 1; r <= it.y1 + 1; ++r)
           {
+            if (PF > 0 && leader && r + PF <= it.y1 + 1)
+            {
+              const int rp = r + PF;
+              for (int c = 0; c < p.nchunks; ++c)
+              {
+                if (p.chunk_up[c]) { if (!(rp & 1)) tma_prefetch_4d(&p.amap[c], p.chunk_c0[c], 0, it.x0 / 2 - 1, rp >> 1); }
+                else               tma_prefetch_3d(&p.amap[c], p.chunk_c0[c], it.x0 - 1, rp);
+              }
+            }
             for (int c = 0; c < p.nchunks; ++c)
             {
               const uint32_t full = full_a + 8 * s;
@@ -622,8 +648,14 @@ cudaError_t conv3x3_tc_launch(const ConvKernelParams& p, int grid, size_t smem_b
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  conv3x3_tc_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, p);
 }
 
 } // namespace oidnb200

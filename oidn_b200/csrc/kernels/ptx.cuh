@@ -101,6 +101,29 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
                : "memory");
 }
 
+// Programmatic dependent launch: let the next grid in the stream start its prologue / wait for the
+// previous grid's memory before touching activations.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// L2 prefetch of a tile (no shared-memory destination): shortens the latency of the TMA load that follows
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               :: "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // smem (shared::cta) -> global, clipped at the tensor bounds; completion tracked by bulk groups.
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2)
 {
