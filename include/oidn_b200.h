@@ -129,6 +129,10 @@ typedef struct oidnb200_tile_plan
 } oidnb200_tile_plan;
 OIDNB200_API void oidnb200PlanTiles(int H, int W, int largeModel, int deviceMinAlignment, int numEngines,
                                     long maxTilePixels, oidnb200_tile_plan* plan);
+/* This backend's default search (device parameter "tilePolicy" = 1): same geometry rules, but the
+ * grid whose tile count is divisible by numUnits (engines x shards) and recomputes the fewest pixels. */
+OIDNB200_API void oidnb200PlanTilesMinOverlap(int H, int W, int largeModel, int deviceMinAlignment, int numUnits,
+                                              long maxTilePixels, oidnb200_tile_plan* plan);
 /* Tile rectangles of a plan, 12 ints each (hSrc,wSrc,hBuf,wBuf,H1,W1,hOutBuf,wOutBuf,hDst,wDst,H2,W2);
  * returns the tile count; writes at most maxTiles tiles. */
 OIDNB200_API int oidnb200EnumerateTiles(const oidnb200_tile_plan* plan, int* out, int maxTiles);

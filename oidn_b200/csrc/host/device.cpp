@@ -20,9 +20,11 @@ Device::Device(const std::vector<int>& ids, const std::vector<void*>& streams)
   for (size_t i = 0; i < ids.size(); ++i)
     for (size_t j = i + 1; j < ids.size(); ++j)
       if (ids[i] == ids[j]) throw Exception(Error::InvalidArgument, "duplicate CUDA device ID");
-  // 4K (3840x2176 tile buffer) is one tile on a B200; the reference's default of 2160x2160
-  // (core/unet_filter.h:39) exists for GPUs with little memory.
-  maxTilePixels = 3840L * 2176L;
+  // Up to 8K (7680x4320: a 7.6 GB arena for the base UNet, every tensor < 4 GiB) is one tile on a
+  // B200's 180 GB; the reference's default of 2160x2160 (core/unet_filter.h:39) exists for GPUs
+  // with little memory. Tiling is then driven by the number of engines / shards only.
+  maxTilePixels = 7680L * 4352L;
+  if (const char* e = getenv("OIDN_B200_TILE_POLICY")) tilePolicy = atoi(e);
   if (const char* e = getenv("OIDN_B200_MAX_TILE_PIXELS")) maxTilePixels = atol(e);
   if (const char* e = getenv("OIDN_B200_WEIGHTS_DIR")) weightsDir = e;
   if (const char* e = getenv("OIDN_VERBOSE")) verbose = atoi(e);
@@ -116,6 +118,7 @@ void Device::setInt(const std::string& name, int value)
   if (name == "verbose") verbose = value;
   else if (name == "profile") profile = value; // backend specific: per-op CUDA-event timing
   else if (name == "maxTilePixels") maxTilePixels = value; // backend specific
+  else if (name == "tilePolicy") tilePolicy = value;       // backend specific: 0 = reference search, 1 = fewest recomputed pixels
   else if (committed) throw Exception(Error::InvalidOperation, "device can be committed only once");
   else throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
 }
@@ -131,6 +134,7 @@ int Device::getInt(const std::string& name) const
   if (name == "profile") return profile;
   if (name == "numSubdevices") return (int)deviceIDs.size();
   if (name == "maxTilePixels") return (int)maxTilePixels;
+  if (name == "tilePolicy") return tilePolicy;
   if (name == "systemMemorySupported" || name == "managedMemorySupported")
   {
     int v = 0;

@@ -64,6 +64,7 @@ private:
   int verbose = 0;
   int profile = 0;
   long maxTilePixels;
+  int tilePolicy = 1;
   std::string weightsDir;
   std::mutex mutex;
   Error errorCode = Error::None;

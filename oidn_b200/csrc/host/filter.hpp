@@ -80,6 +80,9 @@ struct TileRect
 // Same search as core/unet_filter.cpp:283-326. `fits` is the memory test (buildModel).
 TilePlan planTiles(int H, int W, bool largeModel, int deviceMinAlignment, int numEngines, long maxTilePixels,
                    const std::function<bool(const TilePlan&)>& fits);
+// Own search (device parameter tilePolicy=1, the default): the grid with the fewest recomputed pixels.
+TilePlan planTilesMinOverlap(int H, int W, bool largeModel, int deviceMinAlignment, int numUnits, long maxTilePixels,
+                             const std::function<bool(const TilePlan&)>& fits);
 std::vector<TileRect> enumerateTiles(const TilePlan& plan);
 
 class UNetFilter : public Filter

@@ -21,9 +21,10 @@ import numpy as np
 from . import api, capi
 
 
-def tiles_of_rank(H, W, large, world, rank, max_tile_pixels=3840 * 2176):
-  """(plan, [tile rects of this rank]) -- host logic only, usable without a GPU."""
-  plan, tiles = api.plan_tiles(H, W, large, 1, world, max_tile_pixels)
+def tiles_of_rank(H, W, large, world, rank, max_tile_pixels=7680 * 4352, policy=1):
+  """(plan, [tile rects of this rank]) -- host logic only, usable without a GPU. Defaults = the
+  device defaults (maxTilePixels, tilePolicy), so this is the plan every rank's filter builds."""
+  plan, tiles = api.plan_tiles(H, W, large, 1, world, max_tile_pixels, policy)
   return plan, [t for i, t in enumerate(tiles) if i % world == rank]
 
 
@@ -117,32 +118,50 @@ def bench_main(args, rank, world, local_rank):
   W, H, K, Wm = args.width, args.height, args.steps, args.warmup
   tza = weights.model_tza("base", 9, seed=0)
   peaks, peaks_src = B.load_peaks()
-  stream = torch.cuda.Stream()
   sampler = B.ClockSampler(local_rank) if rank == 0 else None
+  frame = synth.benchmark_images(W, H, hdr=True, seed=1) if rank == 0 else None
+
+  # Two frames in flight (a renderer double-buffers its frame): two device/stream/filter sets, frames
+  # alternate between them, so the peers' NVLink reads of frame f+1 overlap the convolutions of frame f.
+  # Collectives are issued in frame order by every rank.
+  sets = []
+  for i in range(2):
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+      dev = api.Device((local_rank,), streams=[stream.cuda_stream]).commit()
+      sf = ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, frame=frame)
+    sets.append((stream, dev, sf))
+  info = sets[0][2].filter.info()
+  ntiles = info["tileCountH"] * info["tileCountW"]
+
+  def run_frame(i):
+    stream, _, sf = sets[i % 2]
+    with torch.cuda.stream(stream):
+      sf.execute_async()
+
+  sA, sB = sets[0][0], sets[1][0]
+  for i in range(max(Wm, 2)):
+    run_frame(i)
+  torch.cuda.synchronize(); dist.barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  join = torch.cuda.Event()
+  t0 = time.time()
+  e0.record(sA)
+  sB.wait_event(e0)                 # neither stream starts a timed frame before e0
+  for i in range(K):
+    run_frame(i)
+  join.record(sB)
+  sA.wait_event(join)
+  e1.record(sA)                     # after the last frame of both streams
+  torch.cuda.synchronize(); dist.barrier()
+  t1 = time.time()
+  ms = torch.tensor([e0.elapsed_time(e1) / K], device="cuda")
+  dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  ms = float(ms.item())
+
+  # per-op times on this rank's tiles (roofline of the dominant kernel, rank 0's share): one set alone
+  stream, dev, sf = sets[0]
   with torch.cuda.stream(stream):
-    dev = api.Device((local_rank,), streams=[stream.cuda_stream]).commit()
-    frame = synth.benchmark_images(W, H, hdr=True, seed=1) if rank == 0 else None
-    sf = ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, frame=frame)
-    info = sf.filter.info()
-    ntiles = info["tileCountH"] * info["tileCountW"]
-    my_tiles = len([i for i in range(ntiles) if i % world == rank])
-
-    for _ in range(Wm):
-      sf.execute_async()
-    torch.cuda.synchronize(); dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    e0.record(stream)
-    for _ in range(K):
-      sf.execute_async()
-    e1.record(stream)
-    torch.cuda.synchronize(); dist.barrier()
-    t1 = time.time()
-    ms = torch.tensor([e0.elapsed_time(e1) / K], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-
-    # per-op times on this rank's tiles (roofline of the dominant kernel, rank 0's share)
     dev.set("profile", 1)
     sf.execute_async(); torch.cuda.synchronize(); sf.filter.profile()
     for _ in range(K):
@@ -150,39 +169,43 @@ def bench_main(args, rank, world, local_rank):
     torch.cuda.synchronize()
     prof = sf.filter.profile()
     dev.set("profile", 0)
-    dist.barrier()
+  dist.barrier()
 
-    # end to end: the frame arrives in rank 0's pinned host memory and the result returns there
-    e2e = None
-    if not args.no_e2e:
-      nb = W * H * 12
-      if rank == 0:
-        hin = {k: torch.from_numpy(v).pin_memory() for k, v in frame.items()}
-        hout = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()
-      L = capi.lib()
+  # end to end: frames arrive in rank 0's pinned host memory and the results return there; the two
+  # sets alternate so the PCIe copies of one frame overlap the other frame's execution
+  e2e = None
+  if not args.no_e2e:
+    nb = W * H * 12
+    if rank == 0:
+      hin = {k: torch.from_numpy(v).pin_memory() for k, v in frame.items()}
+      hout = [torch.zeros((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    L = capi.lib()
 
-      def e2e_frame():
+    def e2e_frame(i):
+      stream, _, sf = sets[i % 2]
+      with torch.cuda.stream(stream):
         if rank == 0:
           for k in ("color", "albedo", "normal"):
             L.oidnb200WriteBufferAsync(sf.bufs[k]._h, 0, nb, hin[k].data_ptr())
         sf.execute_async()
         if rank == 0:
-          L.oidnb200ReadBufferAsync(sf.bufs["output"]._h, 0, nb, hout.data_ptr())
-        torch.cuda.synchronize()
-      for _ in range(2):
-        e2e_frame()
-      dist.barrier()
-      w0 = time.perf_counter()
-      for _ in range(K):
-        e2e_frame()
-      dist.barrier()
-      dt = torch.tensor([(time.perf_counter() - w0) / K], device="cuda")
-      dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-      dt = float(dt.item())
-      e2e = {"value": round(W * H / dt / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dt * 1e3, 4),
-             "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": nb,
-             "how": "rank 0: pinned host fp32 frame -> WriteBufferAsync x3, all ranks: sharded execute, rank 0: ReadBufferAsync; "
-                    "synchronised every frame; max over ranks"}
+          L.oidnb200ReadBufferAsync(sf.bufs["output"]._h, 0, nb, hout[i % 2].data_ptr())
+    for i in range(2):
+      e2e_frame(i)
+    torch.cuda.synchronize(); dist.barrier()
+    w0 = time.perf_counter()
+    for i in range(K):
+      if i >= 2:
+        sets[i % 2][0].synchronize()   # the host consumes frame i-2's result before its buffers are reused
+      e2e_frame(i)
+    torch.cuda.synchronize(); dist.barrier()
+    dt = torch.tensor([(time.perf_counter() - w0) / K], device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    e2e = {"value": round(W * H / dt / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dt * 1e3, 4),
+           "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": nb,
+           "how": "rank 0: pinned host fp32 frame -> WriteBufferAsync x3, all ranks: sharded execute, rank 0: ReadBufferAsync; "
+                  "two frame sets alternating (copies of one frame overlap the other's execution); wall clock, max over ranks"}
 
   if rank == 0:
     clocks = sampler.window(t0, t1); sampler.stop()
@@ -206,10 +229,11 @@ def bench_main(args, rank, world, local_rank):
         info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"], ntiles // world)),
       "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
       "gpu_launches": K * (1 + ntiles * info["numOps"]), "clocks": clocks,   # all ranks: autoexposure + every tile's ops
-      "exchange": "CUDA IPC peer mappings of rank 0's frame; NCCL broadcast(4 B) + all_reduce(4 B) per frame",
+      "exchange": "CUDA IPC peer mappings of rank 0's frame; NCCL broadcast(4 B) + all_reduce(4 B) per frame; two frames in flight",
     }
     print(json.dumps(line))
-  sf.release()
-  dev.release()
+  for _, dev, sf in sets:
+    sf.release()
+    dev.release()
   dist.barrier()
   dist.destroy_process_group()

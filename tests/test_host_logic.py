@@ -65,6 +65,31 @@ def test_survey_tilings():
   assert p["tileCountW"] * p["tileCountH"] == 1
 
 
+@pytest.mark.parametrize("H,W", SIZES)
+@pytest.mark.parametrize("large", [False, True])
+@pytest.mark.parametrize("units", [1, 2, 3, 4, 8])
+def test_min_overlap_planner(H, W, large, units):
+  """This backend's default search (tilePolicy=1): same geometry invariants as the reference's plan,
+  tile count divisible by the units (engines x shards), never more work per unit than the reference's."""
+  for max_px in (7680 * 4352, 3840 * 2176, 1000 * 1000):
+    ref, _ = api.plan_tiles(H, W, large, 1, units, max_px, policy=0)
+    got, tiles = api.plan_tiles(H, W, large, 1, units, max_px, policy=1)
+    check_tiles(H, W, got, tiles)
+    n_ref, n_got = ref["tileCountH"] * ref["tileCountW"], got["tileCountH"] * got["tileCountW"]
+    if n_ref % units == 0 and ref["tileH"] * ref["tileW"] <= max_px:   # the reference search found a valid plan
+      assert n_got % units == 0 and got["tileH"] * got["tileW"] <= max_px
+      assert (n_got // units) * got["tileH"] * got["tileW"] <= (n_ref // units) * ref["tileH"] * ref["tileW"]
+    assert got["tileOverlap"] == ref["tileOverlap"] and got["tileAlignment"] == ref["tileAlignment"]
+
+
+def test_min_overlap_tilings_8k():
+  """8K frame on 1/2/4/8 B200s: one tile per GPU, recomputed pixels +0 / +2.5 / +7.1 / +12.3 %."""
+  want = {1: (1, 1, 7680, 4320), 2: (2, 1, 3936, 4320), 4: (2, 2, 3936, 2256), 8: (4, 2, 2064, 2256)}
+  for n, (cw, ch, tw, th) in want.items():
+    p, _ = api.plan_tiles(4320, 7680, False, 1, n, 7680 * 4352, policy=1)
+    assert (p["tileCountW"], p["tileCountH"], p["tileW"], p["tileH"]) == (cw, ch, tw, th), (n, p)
+
+
 def parse(blob):
   msg = C.c_char_p()
   buf = (C.c_char * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
