@@ -70,6 +70,13 @@ OIDNB200_API void oidnb200WriteBuffer(OIDNB200Buffer buffer, size_t byteOffset, 
 OIDNB200_API void oidnb200ReadBufferAsync(OIDNB200Buffer buffer, size_t byteOffset, size_t byteSize, void* dstHostPtr);
 OIDNB200_API void oidnb200WriteBufferAsync(OIDNB200Buffer buffer, size_t byteOffset, size_t byteSize, const void* srcHostPtr);
 OIDNB200_API void oidnb200ReleaseBuffer(OIDNB200Buffer buffer);
+/* Copy-engine transfer of an image rectangle (rows of widthBytes, row pitches in bytes) in the
+ * device's stream order, between any two of: this GPU's memory, a peer GPU's memory (imported
+ * buffer / peer-enabled pointer: NVLink), pinned host memory. Used to stage a tile of a frame that
+ * lives on another GPU or on the host without occupying SMs (no counterpart in oidn.h, whose
+ * buffers only copy linearly: oidnReadBufferAsync / oidnWriteBufferAsync, oidn.h:352-369). */
+OIDNB200_API void oidnb200CopyRectAsync(OIDNB200Device device, void* dst, size_t dstPitch, const void* src, size_t srcPitch,
+                                        size_t widthBytes, size_t height);
 /* Cross-process sharing of a device buffer on one node (the role oidnNewSharedBufferFromFD,
  * oidn.h:326-329, plays for external memory): the owner exports a 64-byte CUDA IPC handle, a peer
  * process imports it as a buffer it may read and write over NVLink. Device-storage buffers only. */

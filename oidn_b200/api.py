@@ -82,6 +82,10 @@ class Device:
     h = capi.lib().oidnb200NewBufferWithStorage(self._h, byte_size, storage); _check(self._h)
     return Buffer(self, h)
 
+  def copy_rect_async(self, dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, height):
+    """Copy-engine 2D transfer in stream order (local / peer GPU / pinned host memory)."""
+    capi.lib().oidnb200CopyRectAsync(self._h, dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, height); _check(self._h)
+
   def import_buffer(self, ipc_handle, byte_size):
     """Opens a peer process's exported device buffer (CUDA IPC, same node)."""
     raw = (C.c_char * 64).from_buffer_copy(bytes(ipc_handle))

@@ -101,6 +101,7 @@ FILTER_ABI = {
   "oidnb200ReadBufferAsync": (None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
   "oidnb200WriteBufferAsync": (None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
   "oidnb200ReleaseBuffer": (None, [C.c_void_p]),
+  "oidnb200CopyRectAsync": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
   "oidnb200GetBufferIpcHandle": (None, [C.c_void_p, C.c_void_p]),
   "oidnb200NewSharedBufferFromIpcHandle": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_size_t]),
   "oidnb200NewFilter": (C.c_void_p, [C.c_void_p, C.c_char_p]),

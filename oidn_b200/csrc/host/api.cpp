@@ -195,6 +195,18 @@ void oidnb200WriteBuffer(OIDNB200Buffer b, size_t off, size_t n, const void* src
 void oidnb200ReadBufferAsync(OIDNB200Buffer b, size_t off, size_t n, void* dst) { bufferCopy(b, off, n, dst, nullptr, true, false); }
 void oidnb200WriteBufferAsync(OIDNB200Buffer b, size_t off, size_t n, const void* src) { bufferCopy(b, off, n, nullptr, src, false, false); }
 
+void oidnb200CopyRectAsync(OIDNB200Device d, void* dst, size_t dstPitch, const void* src, size_t srcPitch,
+                           size_t widthBytes, size_t height)
+{
+  guarded(d, [&] {
+    d->impl->checkCommitted();
+    if (widthBytes == 0 || height == 0) return;
+    if (!dst || !src) throw Exception(Error::InvalidArgument, "pointer is null");
+    if (dstPitch < widthBytes || srcPitch < widthBytes) throw Exception(Error::InvalidArgument, "pitch is smaller than the row");
+    d->impl->getEngine(0)->submitCopy2D(dst, dstPitch, src, srcPitch, widthBytes, height);
+  });
+}
+
 void oidnb200ReleaseBuffer(OIDNB200Buffer b)
 {
   if (!b) return;

@@ -84,6 +84,13 @@ void Engine::submitCopy(void* dst, const void* src, size_t bytes)
   checkCuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)), "cudaMemcpyAsync");
 }
 
+void Engine::submitCopy2D(void* dst, size_t dstPitch, const void* src, size_t srcPitch, size_t widthBytes, size_t height)
+{
+  makeCurrent();
+  checkCuda(cudaMemcpy2DAsync(dst, dstPitch, src, srcPitch, widthBytes, height, cudaMemcpyDefault,
+                              static_cast<cudaStream_t>(stream)), "cudaMemcpy2DAsync");
+}
+
 static void CUDART_CB hostFuncTrampoline(void* p)
 {
   std::unique_ptr<std::function<void()>> f(static_cast<std::function<void()>*>(p));

@@ -197,6 +197,7 @@ public:
   void* malloc(size_t bytes, Storage storage = Storage::Device);
   void free(void* ptr, Storage storage = Storage::Device);
   void submitCopy(void* dst, const void* src, size_t bytes); // async on the engine's stream
+  void submitCopy2D(void* dst, size_t dstPitch, const void* src, size_t srcPitch, size_t widthBytes, size_t height);
   void submitHostFunc(std::function<void()>&& f);
   void wait();
 

@@ -35,15 +35,22 @@ def broadcast_object(dist, obj, src=0):
 
 
 class ShardedFilter:
-  """RT filter over a frame resident on rank 0, executed by all ranks of the process group."""
+  """RT filter over a frame resident on rank 0, executed by all ranks of the process group.
+
+  stage=True (default): a peer rank moves its tiles with the copy engines -- input rectangles
+  (with overlap) rank 0 -> local staging images before the tile runs, output rectangles local ->
+  rank 0 after it -- so NVLink traffic occupies no SM and overlaps the convolutions of another
+  frame in flight. stage=False: the input/output-process kernels dereference rank 0's memory
+  directly (P2P loads/stores)."""
 
   def __init__(self, dist, torch, device, W, H, tza, hdr=True, quality=api.QUALITY_HIGH, clean_aux=False,
-               aux=True, frame=None):
+               aux=True, frame=None, stage=True):
     self.dist, self.torch, self.dev = dist, torch, device
     self.rank, self.world = dist.get_rank(), dist.get_world_size()
     self.W, self.H, self.hdr = W, H, hdr
     nb = W * H * 12
     names = ("color", "albedo", "normal", "output") if aux else ("color", "output")
+    self.inputs = names[:-1]
     self.bufs = {}
     if self.rank == 0:
       for n in names:
@@ -57,11 +64,13 @@ class ShardedFilter:
     if self.rank != 0:
       for n in names:
         self.bufs[n] = device.import_buffer(handles[n], nb)
+    self.staged = bool(stage) and self.rank != 0
+    self.local = {n: device.new_buffer(nb) for n in names} if self.staged else self.bufs
     self.scale = torch.ones(1, dtype=torch.float32, device="cuda")
     self.token = torch.zeros(1, dtype=torch.float32, device="cuda")
     f = device.new_filter("RT")
     for n in names:
-      f.set_image(n, self.bufs[n], capi.FORMAT_FLOAT3, W, H)
+      f.set_image(n, self.local[n], capi.FORMAT_FLOAT3, W, H)
     f.set("hdr", bool(hdr)); f.set("quality", quality); f.set("cleanAux", bool(clean_aux))
     f.set("numShards", self.world); f.set("shardIndex", self.rank)
     if hdr:
@@ -69,13 +78,30 @@ class ShardedFilter:
     f.set_data("weights", tza)
     f.commit()
     self.filter = f
+    info = f.info()
+    plan, self.tiles = tiles_of_rank(H, W, bool(info["largeModel"]), self.world, self.rank,
+                                     device.get("maxTilePixels"), device.get("tilePolicy"))
+    assert (plan["tileCountH"], plan["tileCountW"], plan["tileH"], plan["tileW"]) == \
+           (info["tileCountH"], info["tileCountW"], info["tileH"], info["tileW"]), (plan, info)
     if self.rank == 0 and hdr:
       L = capi.lib()
       self.ae_scratch = torch.zeros(L.oidnb200_autoexposure_scratch_bytes(H, W), dtype=torch.uint8, device="cuda")
       self.ae_img = capi.Image(self.bufs["color"].data, capi.FORMAT_FLOAT3, W, H, 12, 12 * W)
 
+  def _copy_rects(self, names, to_local):
+    pitch = self.W * 12
+    for t in self.tiles:
+      h, w, nh, nw = (t["hSrc"], t["wSrc"], t["H1"], t["W1"]) if to_local else (t["hDst"], t["wDst"], t["H2"], t["W2"])
+      off = h * pitch + w * 12
+      for n in names:
+        loc, rem = self.local[n].data + off, self.bufs[n].data + off
+        if to_local:
+          self.dev.copy_rect_async(loc, pitch, rem, pitch, nw * 12, nh)
+        else:
+          self.dev.copy_rect_async(rem, pitch, loc, pitch, nw * 12, nh)
+
   def execute_async(self):
-    """Enqueues one frame on the current torch stream of every rank."""
+    """Enqueues one frame on the device's stream of every rank."""
     torch, dist = self.torch, self.dist
     if self.hdr:
       if self.rank == 0:
@@ -86,11 +112,18 @@ class ShardedFilter:
       dist.broadcast(self.scale, src=0)       # also orders the peers after rank 0's frame upload
     else:
       dist.all_reduce(self.token)             # frame-start ordering without a scale
+    if self.staged:
+      self._copy_rects(self.inputs, True)     # NVLink DMA: rank 0 -> local tile inputs (with overlap)
     self.filter.execute_async()
+    if self.staged:
+      self._copy_rects(("output",), False)    # NVLink DMA: local interior rectangles -> rank 0's output
     dist.all_reduce(self.token)               # join: every rank's rectangles are in rank 0's output
 
   def release(self):
     self.filter.release()
+    if self.staged:
+      for b in self.local.values():
+        b.release()
     self.dist.barrier()
     if self.rank != 0:
       for b in self.bufs.values():
@@ -229,7 +262,8 @@ def bench_main(args, rank, world, local_rank):
         info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"], ntiles // world)),
       "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
       "gpu_launches": K * (1 + ntiles * info["numOps"]), "clocks": clocks,   # all ranks: autoexposure + every tile's ops
-      "exchange": "CUDA IPC peer mappings of rank 0's frame; NCCL broadcast(4 B) + all_reduce(4 B) per frame; two frames in flight",
+      "exchange": "CUDA IPC peer mappings of rank 0's frame; peers stage their tile rectangles with copy-engine transfers over "
+                  "NVLink (in: tile + overlap, out: interior); NCCL broadcast(4 B) + all_reduce(4 B) per frame; two frames in flight",
     }
     print(json.dumps(line))
   for _, dev, sf in sets:

@@ -40,6 +40,22 @@ def _worker(rank, world, port, q):
     dist.all_reduce(total)                     # the join: all ranks' rectangles together
     assert int(total.min()) == 1 and int(total.max()) == 1, "ranks' output rectangles must partition the frame"
     out[(H, W, large)] = len(mine)
+    # staged exchange (ShardedFilter stage=True) with an identity "filter": a rank copies its input
+    # rectangles from the owner's frame into zeroed local staging, produces its interior rectangles
+    # from staging only, and copies them back; the joined output must equal the frame.
+    if H * W <= 3840 * 2160:
+      frame = np.arange(H * W, dtype=np.float32).reshape(H, W) % 1021.0
+      local = np.zeros_like(frame)
+      for t in mine:
+        local[t["hSrc"]:t["hSrc"] + t["H1"], t["wSrc"]:t["wSrc"] + t["W1"]] = \
+          frame[t["hSrc"]:t["hSrc"] + t["H1"], t["wSrc"]:t["wSrc"] + t["W1"]]
+      result = np.zeros_like(frame)
+      for t in mine:
+        result[t["hDst"]:t["hDst"] + t["H2"], t["wDst"]:t["wDst"] + t["W2"]] = \
+          local[t["hDst"]:t["hDst"] + t["H2"], t["wDst"]:t["wDst"] + t["W2"]]
+      joined = torch.from_numpy(result)
+      dist.all_reduce(joined)
+      assert np.array_equal(joined.numpy(), frame)
   # handle exchange: rank 0's 64-byte handles reach every rank unchanged
   handles = {"color": bytes(range(64)), "output": bytes(range(64, 128))} if rank == 0 else None
   got = sharded.broadcast_object(dist, handles, 0)
