@@ -50,12 +50,29 @@ def load_peaks():
 
 
 class ClockSampler:
-  """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+  """Samples SM clocks, power and clock-event (throttle) reasons while the timed region runs: NVML polled in
+  this process every ~2 ms (the timed region of a 4K bench is tens of ms), nvidia-smi -lms 100 as fallback."""
   Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+  NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
   def __init__(self, index):
-    self.rows, self.proc = [], None
+    self.rows, self.proc, self.nvml, self.run = [], None, None, True
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      h = None
+      try:
+        import torch
+        h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+      except Exception:
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.nvml, self.h = pynvml, h
+      self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+      self.t = threading.Thread(target=self._poll, daemon=True); self.t.start()
+      return
+    except Exception:
+      self.nvml = None
     try:
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                     "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -63,22 +80,40 @@ class ClockSampler:
     except Exception:
       self.proc = None
 
+  def _poll(self):
+    n = self.nvml
+    bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+            n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+    while self.run:
+      try:
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        try:
+          pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+          pw = 0.0
+        self.rows.append((time.time(), [str(sm), str(self.max_sm), "%.1f" % pw] + ["Active" if r & b else "Not Active" for b in bits]))
+      except Exception:
+        pass
+      time.sleep(0.002)
+
   def _read(self):
     for line in self.proc.stdout:
       self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
   def window(self, t0, t1):
-    rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+    rows = [r for t, r in list(self.rows) if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
     if not rows:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
     sm = sorted(int(float(r[0])) for r in rows if r[0].replace(".", "").isdigit())
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
+    reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
     pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(rows[0][1])) if rows[0][1].replace(".", "").isdigit() else None,
-            "power_w": round(max(pw), 1) if pw else None, "samples": len(rows), "reasons": reasons}
+            "power_w": round(max(pw), 1) if pw else None, "samples": len(rows), "reasons": reasons,
+            "source": "nvml, 2 ms poll" if self.nvml else "nvidia-smi -lms 100"}
 
   def stop(self):
+    self.run = False
     if self.proc:
       self.proc.terminate()
 
@@ -134,7 +169,7 @@ def run_reference(args, rank):
   print(json.dumps({
     "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
     "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
-    "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
     "config": workload_config(args, args.gpus),
     "cpu_baseline": {"value": round(val, 4), "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
     "e2e": {"value": round(val, 4), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -277,7 +312,7 @@ def main():
   line = {
     "metric": METRIC, "value": round(px / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": 1, "steps": K, "warmup": Wm,
     "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-    "dtype": "fp16 storage, fp32 accumulate", "data": "synthetic",
+    "dtype": "f16", "accumulate": "f32", "data": "synthetic",
     "config": dict(workload_config(args, 1), tiles="%dx%d of %dx%d" % (info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"])),
     "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "passes": passes,
   }

@@ -257,7 +257,7 @@ def bench_main(args, rank, world, local_rank):
     line = {
       "metric": B.METRIC, "value": round(W * H / (ms * 1e-3) / 1e6, 1), "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
       "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-      "dtype": "fp16 storage, fp32 accumulate", "data": "synthetic",
+      "dtype": "f16", "accumulate": "f32", "data": "synthetic",
       "config": dict(B.workload_config(args, world), tiles="%dx%d of %dx%d, %d per rank" % (
         info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"], ntiles // world)),
       "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
