@@ -7,9 +7,10 @@ One "step" = one frame through oidnb200ExecuteFilterAsync (autoexposure + input 
 convolutions + output process per tile). N=1: BASELINE.json configs[1] (RT filter, HDR color +
 albedo + normal, 3840x2160, quality=high -> base UNet; there is no large variant for this feature
 set). N>1 (torchrun, one rank per GPU): the 7680x4320 frame of the same filter,
-tile-sharded across the ranks; the frame lives on rank 0's GPU, every rank reads its tiles from and
-writes its output rectangles into rank 0's buffers over NVLink (CUDA IPC peer mappings), the
-autoexposure scalar is broadcast with NCCL and a 4-byte all-reduce joins the frame.
+tile-sharded across the ranks; every rank holds the inputs of its own tiles (tile + overlap), the
+autoexposure bin array is completed with one NCCL all-reduce (~0.5 MB), output rectangles are
+assembled in rank 0's buffer over NVLink (CUDA IPC peer mappings, copy engines) and a 4-byte
+all-reduce joins the frame. `frame_on_rank0` reports the variant where rank 0 holds the whole frame.
 
 Prints ONE JSON line (rank 0). `value` is device-resident throughput (inputs already in HBM), `e2e`
 is the same metric through the public API with pinned host buffers (H2D + D2H inside the timed
@@ -180,7 +181,8 @@ def workload_config(args, n):
   return {"workload": "RT filter, HDR color+albedo+normal fp32, %dx%d, quality=high (base UNet, 16 convs), autoexposure on, "
                       "oidnBenchmark LCG inputs, synthetic He-init TZA weights" % (W, H),
           "width": W, "height": H, "l2": "inputs and every intermediate tensor are larger than the 126 MB L2 (no flush needed)",
-          "sharding": "single GPU" if n == 1 else "tile-sharded across %d ranks, frame resident on rank 0, NVLink peer reads/writes" % n}
+          "sharding": "single GPU" if n == 1 else "tile-sharded across %d ranks; every rank holds its tiles' inputs (tile + overlap), "
+                      "output assembled in rank 0's HBM by NVLink peer copies" % n}
 
 
 def frame_size(args, n):
@@ -199,6 +201,7 @@ def main():
   ap.add_argument("--height", type=int, default=0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-rank0", action="store_true", help="N>1: skip the secondary frame-on-rank-0 measurement")
   args = ap.parse_args()
   args.explicit_size = bool(args.width and args.height)
   rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -151,12 +151,24 @@ OIDNB200_API int oidnb200_output_process_launch(const void* src, int TH, int TW,
                                                 int hdr, int snorm, const oidnb200_image* dst,
                                                 oidnb200_stream stream);
 
-/* Autoexposure (core/autoexposure.h:14-53, devices/gpu/gpu_autoexposure.h:13-164): one launch,
- * result = 0.18 / exp2(mean log2 of the bin luminances > 1e-8) (1 if none) stored to *dst
- * (device float). scratch: device memory of oidnb200_autoexposure_scratch_bytes(H, W). */
+/* Autoexposure (core/autoexposure.h:14-53, devices/gpu/gpu_autoexposure.h:13-164; the reference
+ * uses three launches): result = 0.18 / exp2(mean log2 of the bin luminances > 1e-8) (1 if none)
+ * stored to *dst (device float). Bins are <= 16x16 pixels, bin i covers rows [i*H/nbh, (i+1)*H/nbh).
+ *   oidnb200_autoexposure_launch: the whole image (bins + reduce); scratch = device memory of
+ *     oidnb200_autoexposure_scratch_bytes(H, W) (the bin array).
+ *   oidnb200_autoexposure_bins_launch: log2(mean luminance) of the bins [bin_h0,bin_h1) x
+ *     [bin_w0,bin_w1) of src's bin grid into bins[nbh*nbw] (-inf = bin not counted); only the pixels
+ *     of those bins are read, so a GPU that holds one tile of the frame computes the bins of its tile.
+ *   oidnb200_autoexposure_reduce_launch: folds a complete bin array in a fixed order -> *dst. The
+ *     result depends on the array only (multi-GPU: sum the per-GPU arrays, zeros elsewhere, first). */
+OIDNB200_API void oidnb200_autoexposure_bin_grid(int H, int W, int* num_bins_h, int* num_bins_w);
 OIDNB200_API size_t oidnb200_autoexposure_scratch_bytes(int H, int W);
 OIDNB200_API int oidnb200_autoexposure_launch(const oidnb200_image* src, void* scratch, float* dst,
                                               oidnb200_stream stream);
+OIDNB200_API int oidnb200_autoexposure_bins_launch(const oidnb200_image* src, int bin_h0, int bin_h1, int bin_w0,
+                                                   int bin_w1, float* bins, oidnb200_stream stream);
+OIDNB200_API int oidnb200_autoexposure_reduce_launch(const float* bins, int num_bins, float* dst,
+                                                     oidnb200_stream stream);
 
 /* ImageCopy (core/image_copy.h, devices/gpu/gpu_image_copy.h:15-27): same format and size. */
 OIDNB200_API int oidnb200_image_copy_launch(const oidnb200_image* src, const oidnb200_image* dst,

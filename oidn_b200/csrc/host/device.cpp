@@ -26,6 +26,7 @@ Device::Device(const std::vector<int>& ids, const std::vector<void*>& streams)
   maxTilePixels = 7680L * 4352L;
   if (const char* e = getenv("OIDN_B200_TILE_POLICY")) tilePolicy = atoi(e);
   if (const char* e = getenv("OIDN_B200_MAX_TILE_PIXELS")) maxTilePixels = atol(e);
+  if (const char* e = getenv("OIDN_B200_GRAPH")) graph = atoi(e);
   if (const char* e = getenv("OIDN_B200_WEIGHTS_DIR")) weightsDir = e;
   if (const char* e = getenv("OIDN_VERBOSE")) verbose = atoi(e);
 }
@@ -118,6 +119,7 @@ void Device::setInt(const std::string& name, int value)
   if (name == "verbose") verbose = value;
   else if (name == "profile") profile = value; // backend specific: per-op CUDA-event timing
   else if (name == "maxTilePixels") maxTilePixels = value; // backend specific
+  else if (name == "graph") graph = value;                 // backend specific: 1 = replay frames as a CUDA graph (frame streams)
   else if (name == "tilePolicy") tilePolicy = value;       // backend specific: 0 = reference search, 1 = fewest recomputed pixels
   else if (committed) throw Exception(Error::InvalidOperation, "device can be committed only once");
   else throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
@@ -135,6 +137,7 @@ int Device::getInt(const std::string& name) const
   if (name == "numSubdevices") return (int)deviceIDs.size();
   if (name == "maxTilePixels") return (int)maxTilePixels;
   if (name == "tilePolicy") return tilePolicy;
+  if (name == "graph") return graph;
   if (name == "systemMemorySupported" || name == "managedMemorySupported")
   {
     int v = 0;

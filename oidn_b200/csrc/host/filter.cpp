@@ -1,4 +1,5 @@
 #include "filter.hpp"
+#include <cuda_runtime.h>
 #include <atomic>
 #include <climits>
 #include <cmath>
@@ -273,8 +274,41 @@ void UNetFilter::cleanup()
   tiles.clear();
 }
 
+void UNetFilter::dropFrameGraph()
+{
+  if (frameGraph.exec)
+  {
+    device->getEngine(0)->makeCurrent();
+    cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(frameGraph.exec));
+    frameGraph.exec = nullptr;
+  }
+  frameGraph.key.clear();
+  frameGraph.seen.clear();
+}
+
+// Everything a frame's kernel arguments depend on besides the committed model.
+std::vector<uint64_t> UNetFilter::frameKey() const
+{
+  std::vector<uint64_t> k;
+  for (const Image* im : {&color, &albedo, &normal, &output})
+  {
+    k.push_back((uint64_t)(uintptr_t)im->ptr);
+    k.push_back(((uint64_t)(uint32_t)im->W << 32) | (uint32_t)im->H);
+    k.push_back((uint64_t)im->format);
+    k.push_back((uint64_t)im->pixelStride);
+    k.push_back((uint64_t)im->rowStride);
+  }
+  uint32_t bits;
+  memcpy(&bits, &inputScale, sizeof(bits));
+  k.push_back(bits);
+  k.push_back((uint64_t)(uintptr_t)inputScaleDevPtr);
+  k.push_back(((uint64_t)(uint32_t)numShards << 32) | (uint32_t)shardIndex);
+  return k;
+}
+
 void UNetFilter::freeScratch()
 {
+  dropFrameGraph();
   for (size_t i = 0; i < instances.size(); ++i)
     if (instances[i].scratch)
     {
@@ -583,55 +617,106 @@ void UNetFilter::execute(SyncMode sync)
     }
   };
 
-  // input scale (core/unet_filter.cpp:172-189)
-  if (inputScaleDevPtr)
-    transferFunc->setInputScale(inputScaleDevPtr);
-  else if (std::isnan(inputScale))
-  {
-    if (hdr)
+  const bool profiling = device->getInt("profile") != 0;
+  auto submitFrame = [&]() {
+    // input scale (core/unet_filter.cpp:172-189)
+    if (inputScaleDevPtr)
+      transferFunc->setInputScale(inputScaleDevPtr);
+    else if (std::isnan(inputScale))
     {
-      autoexposure->setSrc(color);
-      device->getEngine(0)->makeCurrent();
-      autoexposure->submit();
-      report(device->getEngine(0));
-      device->submitBarrier();
-      transferFunc->setInputScale(autoexposure->getDstPtr());
+      if (hdr)
+      {
+        autoexposure->setSrc(color);
+        device->getEngine(0)->makeCurrent();
+        autoexposure->submit();
+        report(device->getEngine(0));
+        device->submitBarrier();
+        transferFunc->setInputScale(autoexposure->getDstPtr());
+      }
+      else
+        transferFunc->setInputScale(1.f);
     }
     else
-      transferFunc->setInputScale(1.f);
+      transferFunc->setInputScale(inputScale);
+
+    for (auto& inst : instances)
+    {
+      inst.inputProcess->setSrc(color, albedo, normal);
+      inst.outputProcess->setDst(outputTemp ? outputTemp : output);
+    }
+
+    int tileIndex = 0, globalIndex = 0;
+    for (const TileRect& t : tiles)
+    {
+      if (globalIndex++ % numShards != shardIndex) continue; // another process's tile
+      checkCancel();
+      Instance& inst = instances[tileIndex % numEngines];
+      inst.graph->setProfiling(profiling);
+      inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
+      inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
+      inst.graph->submit();
+      report(device->getEngine(tileIndex % numEngines));
+      ++tileIndex;
+    }
+    device->submitBarrier();
+
+    if (outputTemp)
+    {
+      device->getEngine(0)->makeCurrent();
+      imageCopy->setDst(output);
+      imageCopy->submit();
+      report(device->getEngine(0));
+    }
+  };
+
+  // Frame-stream path: replay (or capture) the frame as one CUDA graph.
+  const bool graphable = device->getInt("graph") != 0 && numEngines == 1 && !progress && !profiling;
+  if (graphable)
+  {
+    Engine* e0 = device->getEngine(0);
+    cudaStream_t st = static_cast<cudaStream_t>(e0->getStream());
+    const std::vector<uint64_t> key = frameKey();
+    e0->makeCurrent();
+    if (frameGraph.exec && frameGraph.key == key)
+      checkCuda(cudaGraphLaunch(static_cast<cudaGraphExec_t>(frameGraph.exec), st), "cudaGraphLaunch");
+    else if (frameGraph.seen != key)
+    {
+      // first frame with these arguments: run it eagerly (also warms one-time kernel attributes)
+      frameGraph.seen = key;
+      submitFrame();
+    }
+    else
+    {
+      if (frameGraph.exec)
+      {
+        cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(frameGraph.exec));
+        frameGraph.exec = nullptr;
+      }
+      cudaGraph_t g = nullptr;
+      checkCuda(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+      try
+      {
+        submitFrame();
+      }
+      catch (...)
+      {
+        cudaStreamEndCapture(st, &g);
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        throw;
+      }
+      checkCuda(cudaStreamEndCapture(st, &g), "cudaStreamEndCapture");
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&exec, g, 0);
+      cudaGraphDestroy(g);
+      checkCuda(ie, "cudaGraphInstantiate");
+      frameGraph.exec = exec;
+      frameGraph.key = key;
+      checkCuda(cudaGraphLaunch(exec, st), "cudaGraphLaunch");
+    }
   }
   else
-    transferFunc->setInputScale(inputScale);
-
-  for (auto& inst : instances)
-  {
-    inst.inputProcess->setSrc(color, albedo, normal);
-    inst.outputProcess->setDst(outputTemp ? outputTemp : output);
-  }
-
-  const bool profiling = device->getInt("profile") != 0;
-  int tileIndex = 0, globalIndex = 0;
-  for (const TileRect& t : tiles)
-  {
-    if (globalIndex++ % numShards != shardIndex) continue; // another process's tile
-    checkCancel();
-    Instance& inst = instances[tileIndex % numEngines];
-    inst.graph->setProfiling(profiling);
-    inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
-    inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
-    inst.graph->submit();
-    report(device->getEngine(tileIndex % numEngines));
-    ++tileIndex;
-  }
-  device->submitBarrier();
-
-  if (outputTemp)
-  {
-    device->getEngine(0)->makeCurrent();
-    imageCopy->setDst(output);
-    imageCopy->submit();
-    report(device->getEngine(0));
-  }
+    submitFrame();
 
   if (profiling)
     for (auto& inst : instances) inst.graph->collectProfile(profile);

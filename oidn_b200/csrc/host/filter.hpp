@@ -179,6 +179,18 @@ private:
   int inplaceParam = 0;
   size_t totalMemoryByteSize = 0;
   std::vector<Graph::OpTime> profile;
+
+  // Frame streams (device parameter "graph" = 1): the launch sequence of a whole frame
+  // is captured into a CUDA graph the second time the filter runs with the same image pointers and
+  // input scale, and replayed with one cudaGraphLaunch afterwards. Pointer / stride / scale changes
+  // re-capture (they are kernel arguments); commit() and scratch reallocation drop the graph.
+  struct FrameGraph
+  {
+    std::vector<uint64_t> key, seen;
+    void* exec = nullptr; // cudaGraphExec_t
+  } frameGraph;
+  std::vector<uint64_t> frameKey() const;
+  void dropFrameGraph();
 };
 
 class RTFilter final : public UNetFilter

@@ -366,33 +366,36 @@ __global__ void __launch_bounds__(256) output_process_vec4_kernel(const OutputPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Autoexposure: one launch. Each warp reduces whole bins (<=16x16 px: lane = column + 16*(row&1),
-// 8 row pairs), keeps log2(mean luminance) of its bins in registers; block partials go to scratch;
-// the last block to finish folds the partials in a fixed order (deterministic) and writes the scale.
+// Autoexposure in two stream-ordered launches:
+//   bins:   each warp reduces whole bins (<=16x16 px: lane = column + 16*(row&1), 8 row pairs) of a
+//           rectangle of the bin grid and stores log2(mean luminance) per bin (-inf = bin not
+//           counted, L <= 1e-8) into the frame's bin array;
+//   reduce: one block folds the complete bin array in a fixed order (fp64) and writes the scale.
+// The result is a function of the bin array only, so it does not depend on which GPU computed
+// which bins: with a frame sharded by tile every rank fills the bins of its own tiles and the
+// arrays are summed (x + 0 = x) before the fold -- bit-identical to one GPU.
 // ------------------------------------------------------------------------------------------------
-struct AutoexposureParams
+struct AeBinsParams
 {
   Img src;
-  int nbh, nbw;
-  float* block_sums;   // [gridDim.x]
-  int* block_counts;   // [gridDim.x]
-  unsigned int* ticket;
-  float* dst;
+  int nbh, nbw;             // bin grid of the whole image
+  int bh0, bh1, bw0, bw1;   // rectangle of bins computed by this launch
+  float* bins;              // [nbh * nbw]
 };
 
 constexpr int kAeThreads = 256;
+constexpr int kAeReduceThreads = 1024;
 
-__global__ void __launch_bounds__(kAeThreads) autoexposure_kernel(const AutoexposureParams p)
+__global__ void __launch_bounds__(kAeThreads) autoexposure_bins_kernel(const AeBinsParams p)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = kAeThreads / 32;
-  const int nbins = p.nbh * p.nbw;
+  const int rw = p.bw1 - p.bw0;
+  const int nbins = (p.bh1 - p.bh0) * rw;
   const int col = lane & 15, rpar = lane >> 4;
-  float wsum = 0.f;
-  int wcount = 0;
   for (int bin = blockIdx.x * nwarps + warp; bin < nbins; bin += gridDim.x * nwarps)
   {
-    const int bi = bin / p.nbw, bj = bin - bi * p.nbw;
+    const int bi = p.bh0 + bin / rw, bj = p.bw0 + bin % rw;
     const int h0 = (int)((long long)bi * p.src.H / p.nbh), h1 = (int)((long long)(bi + 1) * p.src.H / p.nbh);
     const int w0 = (int)((long long)bj * p.src.W / p.nbw), w1 = (int)((long long)(bj + 1) * p.src.W / p.nbw);
     float L = 0.f;
@@ -408,44 +411,40 @@ __global__ void __launch_bounds__(kAeThreads) autoexposure_kernel(const Autoexpo
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
     L /= (float)((h1 - h0) * (w1 - w0));
-    if (L > 1e-8f) { wsum += log2f(L); wcount++; } // identical on all lanes
+    if (lane == 0) p.bins[(size_t)bi * p.nbw + bj] = (L > 1e-8f) ? log2f(L) : -INFINITY;
   }
-  __shared__ float ssum[kAeThreads / 32];
-  __shared__ int scnt[kAeThreads / 32];
-  __shared__ bool last;
-  if (lane == 0) { ssum[warp] = wsum; scnt[warp] = wcount; }
-  __syncthreads();
-  if (threadIdx.x == 0)
+}
+
+__global__ void __launch_bounds__(kAeReduceThreads) autoexposure_reduce_kernel(const float* __restrict__ bins, int nbins,
+                                                                                float* __restrict__ dst)
+{
+  double s = 0.; int c = 0;
+  for (int i = threadIdx.x; i < nbins; i += kAeReduceThreads)
   {
-    float s = 0.f; int c = 0;
-    for (int i = 0; i < nwarps; ++i) { s += ssum[i]; c += scnt[i]; }
-    p.block_sums[blockIdx.x] = s;
-    p.block_counts[blockIdx.x] = c;
-    __threadfence();
-    const unsigned int t = atomicAdd(p.ticket, 1u);
-    last = (t == gridDim.x - 1);
+    const float v = bins[i];
+    if (v > -INFINITY) { s += (double)v; ++c; }
   }
-  __syncthreads();
-  if (last && warp == 0)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
   {
-    __threadfence();
-    double s = 0.; long long c = 0;
-    for (int i = lane; i < (int)gridDim.x; i += 32)
-    {
-      s += (double)reinterpret_cast<volatile float*>(p.block_sums)[i];
-      c += reinterpret_cast<volatile int*>(p.block_counts)[i];
-    }
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  __shared__ double ss[kAeReduceThreads / 32];
+  __shared__ int sc[kAeReduceThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { ss[warp] = s; sc[warp] = c; }
+  __syncthreads();
+  if (warp == 0)
+  {
+    s = ss[lane]; c = sc[lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
       s += __shfl_xor_sync(0xffffffffu, s, o);
       c += __shfl_xor_sync(0xffffffffu, c, o);
     }
-    if (lane == 0)
-    {
-      *p.dst = c > 0 ? 0.18f / exp2f((float)(s / (double)c)) : 1.f;
-      *p.ticket = 0; // re-arm for the next frame
-    }
+    if (lane == 0) *dst = c > 0 ? 0.18f / exp2f((float)(s / (double)c)) : 1.f;
   }
 }
 
@@ -608,33 +607,64 @@ int oidnb200_output_process_launch(const void* src, int TH, int TW, int C, const
   return check_launch("output_process");
 }
 
-size_t oidnb200_autoexposure_scratch_bytes(int H, int W)
+void oidnb200_autoexposure_bin_grid(int H, int W, int* num_bins_h, int* num_bins_w)
 {
-  const int nbins = ((H + 15) / 16) * ((W + 15) / 16);
-  const int g = autoexposure_grid(nbins);
-  return 256 + (size_t)g * 8; // ticket (own 256-B line) + per-block sum and count
+  // core/autoexposure.h:20-24: bins of at most 16x16 pixels
+  if (num_bins_h) *num_bins_h = (H + 15) / 16;
+  if (num_bins_w) *num_bins_w = (W + 15) / 16;
 }
 
-int oidnb200_autoexposure_launch(const oidnb200_image* src, void* scratch, float* dst, oidnb200_stream stream)
+size_t oidnb200_autoexposure_scratch_bytes(int H, int W)
 {
-  AutoexposureParams p;
-  if (!make_img(src, p.src) || !p.src.ptr || !scratch || !dst || p.src.H <= 0 || p.src.W <= 0)
+  const size_t nbins = (size_t)((H + 15) / 16) * ((W + 15) / 16);
+  return (nbins * sizeof(float) + 255) / 256 * 256; // the bin array
+}
+
+int oidnb200_autoexposure_bins_launch(const oidnb200_image* src, int bin_h0, int bin_h1, int bin_w0, int bin_w1,
+                                      float* bins, oidnb200_stream stream)
+{
+  AeBinsParams p;
+  if (!make_img(src, p.src) || !p.src.ptr || !bins || p.src.H <= 0 || p.src.W <= 0)
   {
     set_error("autoexposure: bad arguments");
     return OIDNB200_ERR_INVALID;
   }
   p.nbh = (p.src.H + 15) / 16; p.nbw = (p.src.W + 15) / 16;
-  const int g = autoexposure_grid(p.nbh * p.nbw);
-  uint8_t* s = static_cast<uint8_t*>(scratch);
-  p.ticket = reinterpret_cast<unsigned int*>(s);
-  p.block_sums = reinterpret_cast<float*>(s + 256);
-  p.block_counts = reinterpret_cast<int*>(s + 256 + (size_t)g * 4);
-  p.dst = dst;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // The ticket must start at zero; the kernel re-arms it, the memset covers fresh scratch.
-  cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st);
-  autoexposure_kernel<<<g, kAeThreads, 0, st>>>(p);
-  return check_launch("autoexposure");
+  if (bin_h0 < 0 || bin_w0 < 0 || bin_h1 > p.nbh || bin_w1 > p.nbw || bin_h0 > bin_h1 || bin_w0 > bin_w1)
+  {
+    set_error("autoexposure: bin rectangle outside the image's bin grid");
+    return OIDNB200_ERR_INVALID;
+  }
+  p.bh0 = bin_h0; p.bh1 = bin_h1; p.bw0 = bin_w0; p.bw1 = bin_w1;
+  p.bins = bins;
+  const int n = (bin_h1 - bin_h0) * (bin_w1 - bin_w0);
+  if (n == 0) return 0;
+  autoexposure_bins_kernel<<<autoexposure_grid(n), kAeThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("autoexposure bins");
+}
+
+int oidnb200_autoexposure_reduce_launch(const float* bins, int num_bins, float* dst, oidnb200_stream stream)
+{
+  if (!bins || !dst || num_bins <= 0)
+  {
+    set_error("autoexposure: bad arguments");
+    return OIDNB200_ERR_INVALID;
+  }
+  autoexposure_reduce_kernel<<<1, kAeReduceThreads, 0, static_cast<cudaStream_t>(stream)>>>(bins, num_bins, dst);
+  return check_launch("autoexposure reduce");
+}
+
+int oidnb200_autoexposure_launch(const oidnb200_image* src, void* scratch, float* dst, oidnb200_stream stream)
+{
+  if (!src || !scratch || !dst)
+  {
+    set_error("autoexposure: bad arguments");
+    return OIDNB200_ERR_INVALID;
+  }
+  const int nbh = (src->H + 15) / 16, nbw = (src->W + 15) / 16;
+  const int rc = oidnb200_autoexposure_bins_launch(src, 0, nbh, 0, nbw, static_cast<float*>(scratch), stream);
+  if (rc) return rc;
+  return oidnb200_autoexposure_reduce_launch(static_cast<float*>(scratch), nbh * nbw, dst, stream);
 }
 
 int oidnb200_image_copy_launch(const oidnb200_image* src, const oidnb200_image* dst, oidnb200_stream stream)

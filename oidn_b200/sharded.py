@@ -2,19 +2,32 @@
 
 The reference deals tiles round-robin to the engines of ONE device object (core/unet_filter.cpp:219)
 and joins them with device->submitBarrier() (:178, :243); its only multi-engine backend (SYCL) shares
-USM pointers between the engines. The same scheme with one process per GPU:
+USM pointers between the engines. The same scheme with one process per GPU: every rank builds the
+same tile plan (tile count % world == 0) and executes the tiles whose index % world == rank. Tiles
+write disjoint rectangles of the output, so there is no reduction on the data path. Two ways of
+holding the frame:
 
-  * the frame (color/albedo/normal/output) lives in rank 0's HBM; rank 0 exports the four buffers
-    as CUDA IPC handles and every other rank maps them (NVLink peer mappings);
-  * every rank builds the same tile plan (tile count % world == 0) and executes the tiles whose
-    index % world == rank: its input-process kernel loads the tile straight from rank 0's buffers
-    (P2P loads), its output-process kernel stores the interior rectangle straight into rank 0's
-    output (P2P stores). Tiles write disjoint rectangles, so no reduction is needed;
-  * the one global value, the autoexposure scale, is computed by rank 0 and broadcast (4 bytes,
-    NCCL, stream ordered); a 4-byte all-reduce at the end of the frame is the join (the
-    submitBarrier of the single-process device).
+  source="distributed" (bench.py): every GPU holds the pixels of its own tiles (tile + overlap) --
+    what a multi-GPU renderer produces, and what each rank pulls from host memory over its own PCIe
+    link in the end-to-end path. The one global value, the autoexposure scale, is exchanged exactly:
+    each rank computes log2(mean luminance) of the <=16x16 bins of its tiles
+    (oidnb200_autoexposure_bins_launch) into a zero-filled bin array, an NCCL all-reduce (sum; x + 0
+    = x, ~0.5 MB at 8K) completes the array on every rank, and every rank folds it in the same fixed
+    order (oidnb200_autoexposure_reduce_launch) -- bit-identical to one GPU. Output rectangles are
+    assembled in rank 0's output buffer with copy-engine peer writes over NVLink (CUDA IPC mapping),
+    or go straight to the host frame in the end-to-end path. A 4-byte all-reduce joins the frame.
+
+  source="rank0": the whole frame (color/albedo/normal/output) lives in rank 0's HBM (the
+    single-pointer contract of oidnSetSharedFilterImage); rank 0 exports the four buffers as CUDA IPC
+    handles, runs the autoexposure and broadcasts the scale (4 bytes); the peers either stage their
+    tile rectangles with copy-engine transfers over NVLink (stage=True) or dereference rank 0's
+    memory directly from the input/output-process kernels (stage=False). Rank 0's NVLink egress
+    bounds this mode beyond 2 GPUs (profiles/README.md).
 """
 import ctypes as C
+import mmap
+import os
+import uuid
 
 import numpy as np
 
@@ -28,44 +41,133 @@ def tiles_of_rank(H, W, large, world, rank, max_tile_pixels=7680 * 4352, policy=
   return plan, [t for i, t in enumerate(tiles) if i % world == rank]
 
 
+def bin_grid(H, W):
+  """Autoexposure bin grid of an HxW image (core/autoexposure.h:20-24)."""
+  return (H + 15) // 16, (W + 15) // 16
+
+
+def _first_bin_at_or_after(x, n, size):
+  """Smallest bin index i (0..n) whose first pixel i*size//n is >= x."""
+  i = min(n, (x * n + size - 1) // size)
+  while i > 0 and (i - 1) * size // n >= x:
+    i -= 1
+  while i < n and i * size // n < x:
+    i += 1
+  return i
+
+
+def bins_of_tile(t, H, W):
+  """(bh0, bh1, bw0, bw1): the autoexposure bins owned by a tile = the bins whose first pixel lies in
+  the tile's destination rectangle. Destination rectangles partition the image, so these rectangles
+  partition the bin grid; a bin is at most 16 px and the tile's source rectangle extends >= 96 px
+  past every interior edge, so all pixels of an owned bin are inside the tile's source rectangle."""
+  nbh, nbw = bin_grid(H, W)
+  bh0 = _first_bin_at_or_after(t["hDst"], nbh, H); bh1 = _first_bin_at_or_after(t["hDst"] + t["H2"], nbh, H)
+  bw0 = _first_bin_at_or_after(t["wDst"], nbw, W); bw1 = _first_bin_at_or_after(t["wDst"] + t["W2"], nbw, W)
+  assert bh0 * H // nbh >= t["hSrc"] and bh1 * H // nbh <= t["hSrc"] + t["H1"], (t, bh0, bh1)
+  assert bw0 * W // nbw >= t["wSrc"] and bw1 * W // nbw <= t["wSrc"] + t["W1"], (t, bw0, bw1)
+  return bh0, bh1, bw0, bw1
+
+
 def broadcast_object(dist, obj, src=0):
   box = [obj]
   dist.broadcast_object_list(box, src=src)
   return box[0]
 
 
-class ShardedFilter:
-  """RT filter over a frame resident on rank 0, executed by all ranks of the process group.
+class SharedHostFrame:
+  """Images of one frame in host memory shared by all ranks of the node: a POSIX shared-memory file
+  mapped by every process and page-locked in each (cudaHostRegister), so every GPU moves its own
+  tiles over its own PCIe link. Falls back to private pinned memory per rank (`shared` False) when
+  /dev/shm cannot hold the frame."""
 
-  stage=True (default): a peer rank moves its tiles with the copy engines -- input rectangles
-  (with overlap) rank 0 -> local staging images before the tile runs, output rectangles local ->
-  rank 0 after it -- so NVLink traffic occupies no SM and overlaps the convolutions of another
-  frame in flight. stage=False: the input/output-process kernels dereference rank 0's memory
-  directly (P2P loads/stores)."""
+  def __init__(self, dist, torch, names, H, W):
+    self.names, self.H, self.W = tuple(names), H, W
+    self.nb = H * W * 12
+    rank = dist.get_rank()
+    total = self.nb * len(self.names)
+    path = None
+    if rank == 0:
+      path = "/dev/shm/oidnb200_%s" % uuid.uuid4().hex
+      try:
+        fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+        os.posix_fallocate(fd, 0, total)
+        os.close(fd)
+      except OSError:
+        try:
+          os.unlink(path)
+        except OSError:
+          pass
+        path = None
+    path = broadcast_object(dist, path, 0)
+    self.shared = path is not None
+    self._registered = None
+    self._torch = torch
+    if self.shared:
+      fd = os.open(path, os.O_RDWR)
+      self._map = mmap.mmap(fd, total)
+      os.close(fd)
+      dist.barrier()
+      if rank == 0:
+        os.unlink(path)   # the mappings keep it alive; nothing is left behind if a rank dies
+      base = np.frombuffer(self._map, dtype=np.uint8)
+      ptr = base.ctypes.data
+      rc = torch.cuda.cudart().cudaHostRegister(ptr, total, 0)
+      if int(rc) != 0:
+        raise RuntimeError("cudaHostRegister of the shared host frame failed: %s" % rc)
+      self._registered = ptr
+      self.images = {n: base[i * self.nb:(i + 1) * self.nb].view(np.float32).reshape(H, W, 3) for i, n in enumerate(self.names)}
+    else:
+      self._pinned = {n: torch.zeros((H, W, 3), dtype=torch.float32).pin_memory() for n in self.names}
+      self.images = {n: t.numpy() for n, t in self._pinned.items()}
+
+  def ptr(self, name):
+    return self.images[name].ctypes.data
+
+  def release(self):
+    if self._registered is not None:
+      self._torch.cuda.cudart().cudaHostUnregister(self._registered)
+      self._registered = None
+    self.images = {}
+
+
+class ShardedFilter:
+  """RT filter over one frame, executed by all ranks of the process group (see the module docstring).
+
+  frame: dict of full-frame float32 HxWx3 arrays. source="rank0": given on rank 0 only and uploaded
+  there. source="distributed": given on every rank (or None to leave the local tile inputs to
+  upload_tiles()); each rank uploads only the source rectangles of its own tiles."""
 
   def __init__(self, dist, torch, device, W, H, tza, hdr=True, quality=api.QUALITY_HIGH, clean_aux=False,
-               aux=True, frame=None, stage=True):
+               aux=True, frame=None, stage=True, source="rank0"):
+    assert source in ("rank0", "distributed")
     self.dist, self.torch, self.dev = dist, torch, device
     self.rank, self.world = dist.get_rank(), dist.get_world_size()
-    self.W, self.H, self.hdr = W, H, hdr
+    self.W, self.H, self.hdr, self.source = W, H, hdr, source
     nb = W * H * 12
     names = ("color", "albedo", "normal", "output") if aux else ("color", "output")
     self.inputs = names[:-1]
     self.bufs = {}
+    shared_names = names if source == "rank0" else ("output",)   # buffers rank 0 exports to the peers
     if self.rank == 0:
-      for n in names:
+      for n in shared_names:
         self.bufs[n] = device.new_buffer(nb)
-        if frame is not None and n in frame:
+        if source == "rank0" and frame is not None and n in frame:
           self.bufs[n].write(frame[n])
-      handles = {n: self.bufs[n].ipc_handle() for n in names}
+      handles = {n: self.bufs[n].ipc_handle() for n in shared_names}
     else:
       handles = None
     handles = broadcast_object(dist, handles, 0)
     if self.rank != 0:
-      for n in names:
+      for n in shared_names:
         self.bufs[n] = device.import_buffer(handles[n], nb)
-    self.staged = bool(stage) and self.rank != 0
-    self.local = {n: device.new_buffer(nb) for n in names} if self.staged else self.bufs
+    if source == "rank0":
+      self.staged = bool(stage) and self.rank != 0
+      self.local = {n: device.new_buffer(nb) for n in names} if self.staged else self.bufs
+    else:
+      self.staged = False
+      self.local = {n: device.new_buffer(nb) for n in self.inputs}
+      self.local["output"] = self.bufs["output"] if self.rank == 0 else device.new_buffer(nb)
     self.scale = torch.ones(1, dtype=torch.float32, device="cuda")
     self.token = torch.zeros(1, dtype=torch.float32, device="cuda")
     f = device.new_filter("RT")
@@ -83,15 +185,29 @@ class ShardedFilter:
                                      device.get("maxTilePixels"), device.get("tilePolicy"))
     assert (plan["tileCountH"], plan["tileCountW"], plan["tileH"], plan["tileW"]) == \
            (info["tileCountH"], info["tileCountW"], info["tileH"], info["tileW"]), (plan, info)
-    if self.rank == 0 and hdr:
-      L = capi.lib()
+    L = capi.lib()
+    if hdr and source == "rank0" and self.rank == 0:
       self.ae_scratch = torch.zeros(L.oidnb200_autoexposure_scratch_bytes(H, W), dtype=torch.uint8, device="cuda")
       self.ae_img = capi.Image(self.bufs["color"].data, capi.FORMAT_FLOAT3, W, H, 12, 12 * W)
+    if hdr and source == "distributed":
+      nbh, nbw = bin_grid(H, W)
+      self.nbins = nbh * nbw
+      self.bins_local = torch.zeros(self.nbins, dtype=torch.float32, device="cuda")   # zeros outside the own bins
+      self.bins_all = torch.zeros(self.nbins, dtype=torch.float32, device="cuda")
+      self.bin_rects = [bins_of_tile(t, H, W) for t in self.tiles]
+      self.ae_img = capi.Image(self.local["color"].data, capi.FORMAT_FLOAT3, W, H, 12, 12 * W)
+    if source == "distributed" and frame is not None:
+      self.upload_tiles({n: frame[n].ctypes.data for n in self.inputs})
+      self.dev.sync()
+
+  # ---- rectangle transfers (copy engines, stream ordered) ------------------------------------------
+  def _rect(self, t, src):
+    return (t["hSrc"], t["wSrc"], t["H1"], t["W1"]) if src else (t["hDst"], t["wDst"], t["H2"], t["W2"])
 
   def _copy_rects(self, names, to_local):
     pitch = self.W * 12
     for t in self.tiles:
-      h, w, nh, nw = (t["hSrc"], t["wSrc"], t["H1"], t["W1"]) if to_local else (t["hDst"], t["wDst"], t["H2"], t["W2"])
+      h, w, nh, nw = self._rect(t, to_local)
       off = h * pitch + w * 12
       for n in names:
         loc, rem = self.local[n].data + off, self.bufs[n].data + off
@@ -100,15 +216,49 @@ class ShardedFilter:
         else:
           self.dev.copy_rect_async(rem, pitch, loc, pitch, nw * 12, nh)
 
-  def execute_async(self):
-    """Enqueues one frame on the device's stream of every rank."""
-    torch, dist = self.torch, self.dist
+  def upload_tiles(self, host_ptrs):
+    """distributed: host frame (full-frame float3 images, pinned or not) -> the source rectangles of
+    this rank's tiles in its local images. host_ptrs: {image name: address of pixel (0,0)}."""
+    pitch = self.W * 12
+    for t in self.tiles:
+      h, w, nh, nw = self._rect(t, True)
+      off = h * pitch + w * 12
+      for n in self.inputs:
+        self.dev.copy_rect_async(self.local[n].data + off, pitch, host_ptrs[n] + off, pitch, nw * 12, nh)
+
+  def download_tiles(self, host_output_ptr):
+    """distributed: this rank's output rectangles -> the host output frame."""
+    pitch = self.W * 12
+    for t in self.tiles:
+      h, w, nh, nw = self._rect(t, False)
+      off = h * pitch + w * 12
+      self.dev.copy_rect_async(host_output_ptr + off, pitch, self.local["output"].data + off, pitch, nw * 12, nh)
+
+  # ---- one frame ------------------------------------------------------------------------------------
+  def execute_async(self, assemble=True):
+    """Enqueues one frame on the device's stream of every rank. assemble=False (distributed only)
+    leaves every rank's output rectangles in its local output image (the caller downloads them)."""
+    torch, dist, L = self.torch, self.dist, capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    if self.source == "distributed":
+      if self.hdr:
+        for (bh0, bh1, bw0, bw1) in self.bin_rects:
+          if L.oidnb200_autoexposure_bins_launch(C.byref(self.ae_img), bh0, bh1, bw0, bw1, self.bins_local.data_ptr(), st) != 0:
+            raise RuntimeError(L.oidnb200_last_error().decode())
+        self.bins_all.copy_(self.bins_local)
+        dist.all_reduce(self.bins_all)          # the exchange step: every rank gets the complete bin array
+        if L.oidnb200_autoexposure_reduce_launch(self.bins_all.data_ptr(), self.nbins, self.scale.data_ptr(), st) != 0:
+          raise RuntimeError(L.oidnb200_last_error().decode())
+      self.filter.execute_async()
+      if assemble and self.rank != 0:
+        self._copy_rects(("output",), False)    # NVLink DMA: local interior rectangles -> rank 0's output
+      dist.all_reduce(self.token)               # join: every rank's rectangles are where they belong
+      return
     if self.hdr:
       if self.rank == 0:
-        rc = capi.lib().oidnb200_autoexposure_launch(C.byref(self.ae_img), self.ae_scratch.data_ptr(),
-                                                     self.scale.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        rc = L.oidnb200_autoexposure_launch(C.byref(self.ae_img), self.ae_scratch.data_ptr(), self.scale.data_ptr(), st)
         if rc != 0:
-          raise RuntimeError(capi.lib().oidnb200_last_error().decode())
+          raise RuntimeError(L.oidnb200_last_error().decode())
       dist.broadcast(self.scale, src=0)       # also orders the peers after rank 0's frame upload
     else:
       dist.all_reduce(self.token)             # frame-start ordering without a scale
@@ -121,9 +271,9 @@ class ShardedFilter:
 
   def release(self):
     self.filter.release()
-    if self.staged:
-      for b in self.local.values():
-        b.release()
+    own = [b for n, b in self.local.items() if b is not self.bufs.get(n)]
+    for b in own:
+      b.release()
     self.dist.barrier()
     if self.rank != 0:
       for b in self.bufs.values():
@@ -137,7 +287,6 @@ class ShardedFilter:
 def bench_main(args, rank, world, local_rank):
   """bench.py's N>1 arm (launched by torchrun, one rank per GPU)."""
   import json
-  import os
   import time
 
   import torch
@@ -152,45 +301,67 @@ def bench_main(args, rank, world, local_rank):
   tza = weights.model_tza("base", 9, seed=0)
   peaks, peaks_src = B.load_peaks()
   sampler = B.ClockSampler(local_rank) if rank == 0 else None
-  frame = synth.benchmark_images(W, H, hdr=True, seed=1) if rank == 0 else None
+  nb = W * H * 12
+
+  # The frame in host memory, shared by all ranks; rank 0 fills it (oidnBenchmark LCG images).
+  host = SharedHostFrame(dist, torch, ("color", "albedo", "normal", "output"), H, W)
+  if rank == 0 or not host.shared:
+    frame = synth.benchmark_images(W, H, hdr=True, seed=1)
+    for k, v in frame.items():
+      host.images[k][...] = v
+    del frame
+  dist.barrier()
+  frame = {k: host.images[k] for k in ("color", "albedo", "normal")}
 
   # Two frames in flight (a renderer double-buffers its frame): two device/stream/filter sets, frames
-  # alternate between them, so the peers' NVLink reads of frame f+1 overlap the convolutions of frame f.
-  # Collectives are issued in frame order by every rank.
-  sets = []
-  for i in range(2):
-    stream = torch.cuda.Stream()
-    with torch.cuda.stream(stream):
-      dev = api.Device((local_rank,), streams=[stream.cuda_stream]).commit()
-      sf = ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, frame=frame)
-    sets.append((stream, dev, sf))
-  info = sets[0][2].filter.info()
-  ntiles = info["tileCountH"] * info["tileCountW"]
+  # alternate between them, so the exchange and the copies of frame f+1 overlap the convolutions of
+  # frame f. Collectives are issued in frame order by every rank.
+  def make_sets(source):
+    sets = []
+    for _ in range(2):
+      stream = torch.cuda.Stream()
+      with torch.cuda.stream(stream):
+        dev = api.Device((local_rank,), streams=[stream.cuda_stream]).commit()
+        sf = ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, source=source,
+                           frame=frame if (source == "distributed" or rank == 0) else None)
+      sets.append((stream, dev, sf))
+    return sets
 
-  def run_frame(i):
+  def timed(sets, frame_fn, wall=False):
+    """K frames alternating between the two sets; device time (events) or wall clock, max over ranks."""
+    sA, sB = sets[0][0], sets[1][0]
+    for i in range(max(Wm, 2)):
+      frame_fn(sets, i)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    join = torch.cuda.Event()
+    t0 = time.time(); w0 = time.perf_counter()
+    e0.record(sA)
+    sB.wait_event(e0)                 # neither stream starts a timed frame before e0
+    for i in range(K):
+      if wall and i >= 2:
+        sets[i % 2][0].synchronize()  # the host consumes frame i-2's result before its buffers are reused
+      frame_fn(sets, i)
+    join.record(sB)
+    sA.wait_event(join)
+    e1.record(sA)                     # after the last frame of both streams
+    torch.cuda.synchronize(); dist.barrier()
+    t1 = time.time()
+    per = (time.perf_counter() - w0) * 1e3 / K if wall else e0.elapsed_time(e1) / K
+    ms = torch.tensor([per], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), t0, t1
+
+  def run_frame(sets, i):
     stream, _, sf = sets[i % 2]
     with torch.cuda.stream(stream):
       sf.execute_async()
 
-  sA, sB = sets[0][0], sets[1][0]
-  for i in range(max(Wm, 2)):
-    run_frame(i)
-  torch.cuda.synchronize(); dist.barrier()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  join = torch.cuda.Event()
-  t0 = time.time()
-  e0.record(sA)
-  sB.wait_event(e0)                 # neither stream starts a timed frame before e0
-  for i in range(K):
-    run_frame(i)
-  join.record(sB)
-  sA.wait_event(join)
-  e1.record(sA)                     # after the last frame of both streams
-  torch.cuda.synchronize(); dist.barrier()
-  t1 = time.time()
-  ms = torch.tensor([e0.elapsed_time(e1) / K], device="cuda")
-  dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-  ms = float(ms.item())
+  sets = make_sets("distributed")
+  info = sets[0][2].filter.info()
+  ntiles = info["tileCountH"] * info["tileCountW"]
+  ms, t0, t1 = timed(sets, run_frame)
+  clocks = sampler.window(t0, t1) if rank == 0 else None
 
   # per-op times on this rank's tiles (roofline of the dominant kernel, rank 0's share): one set alone
   stream, dev, sf = sets[0]
@@ -204,44 +375,47 @@ def bench_main(args, rank, world, local_rank):
     dev.set("profile", 0)
   dist.barrier()
 
-  # end to end: frames arrive in rank 0's pinned host memory and the results return there; the two
-  # sets alternate so the PCIe copies of one frame overlap the other frame's execution
+  # end to end: the frame is in (shared, pinned) host memory and the result returns there; every rank
+  # moves the rectangles of its own tiles over its own PCIe link
   e2e = None
   if not args.no_e2e:
-    nb = W * H * 12
-    if rank == 0:
-      hin = {k: torch.from_numpy(v).pin_memory() for k, v in frame.items()}
-      hout = [torch.zeros((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
-    L = capi.lib()
+    hin = {k: host.ptr(k) for k in ("color", "albedo", "normal")}
+    hout = host.ptr("output")
+    my_in = sum(t["H1"] * t["W1"] for t in sets[0][2].tiles) * 36
+    my_out = sum(t["H2"] * t["W2"] for t in sets[0][2].tiles) * 12
 
-    def e2e_frame(i):
+    def e2e_frame(sets, i):
       stream, _, sf = sets[i % 2]
       with torch.cuda.stream(stream):
-        if rank == 0:
-          for k in ("color", "albedo", "normal"):
-            L.oidnb200WriteBufferAsync(sf.bufs[k]._h, 0, nb, hin[k].data_ptr())
-        sf.execute_async()
-        if rank == 0:
-          L.oidnb200ReadBufferAsync(sf.bufs["output"]._h, 0, nb, hout[i % 2].data_ptr())
-    for i in range(2):
-      e2e_frame(i)
-    torch.cuda.synchronize(); dist.barrier()
-    w0 = time.perf_counter()
-    for i in range(K):
-      if i >= 2:
-        sets[i % 2][0].synchronize()   # the host consumes frame i-2's result before its buffers are reused
-      e2e_frame(i)
-    torch.cuda.synchronize(); dist.barrier()
-    dt = torch.tensor([(time.perf_counter() - w0) / K], device="cuda")
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.item())
-    e2e = {"value": round(W * H / dt / 1e6, 1), "unit": "Mpix/s", "ms_per_step": round(dt * 1e3, 4),
-           "h2d_bytes_per_step": 3 * nb, "d2h_bytes_per_step": nb,
-           "how": "rank 0: pinned host fp32 frame -> WriteBufferAsync x3, all ranks: sharded execute, rank 0: ReadBufferAsync; "
-                  "two frame sets alternating (copies of one frame overlap the other's execution); wall clock, max over ranks"}
+        sf.upload_tiles(hin)
+        sf.execute_async(assemble=False)
+        sf.download_tiles(hout)
+
+    dt, _, _ = timed(sets, e2e_frame, wall=True)
+    traffic = torch.tensor([float(my_in), float(my_out)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(traffic)
+    e2e = {"value": round(W * H / dt / 1e3, 1), "unit": "Mpix/s", "ms_per_step": round(dt, 4),
+           "h2d_bytes_per_step": int(traffic[0].item()), "d2h_bytes_per_step": int(traffic[1].item()),
+           "host_frame": "one frame in POSIX shared memory, page-locked by every rank" if host.shared
+                         else "private pinned copy of the frame per rank (/dev/shm too small)",
+           "how": "every rank: 2D copies of its tiles' source rectangles (with overlap) from the pinned host frame, sharded "
+                  "execute (autoexposure bins all-reduce), 2D copies of its output rectangles into the host output frame; "
+                  "all ranks' bytes summed; two frame sets alternating; wall clock, max over ranks"}
+  for _, dev, sf in sets:
+    sf.release(); dev.release()
+
+  # the frame held by rank 0 alone (single-pointer contract): reported next to the headline
+  on_rank0 = None
+  if not args.no_rank0:
+    sets0 = make_sets("rank0")
+    ms0, _, _ = timed(sets0, run_frame)
+    on_rank0 = {"value": round(W * H / ms0 / 1e3, 1), "unit": "Mpix/s", "ms_per_step": round(ms0, 4),
+                "how": "whole frame in rank 0's HBM; peers pull tile rectangles / push output rectangles with copy engines over NVLink"}
+    for _, dev, sf in sets0:
+      sf.release(); dev.release()
 
   if rank == 0:
-    clocks = sampler.window(t0, t1); sampler.stop()
+    sampler.stop()
     conv_ms = sum(m for _, kind, _, m in prof if kind == 0) / K
     conv_launches = sum(n for _, kind, n, _ in prof if kind == 0) // K
     # rank 0's tiles: algorithmic FLOPs of the pixels it outputs
@@ -260,14 +434,14 @@ def bench_main(args, rank, world, local_rank):
       "dtype": "f16", "accumulate": "f32", "data": "synthetic",
       "config": dict(B.workload_config(args, world), tiles="%dx%d of %dx%d, %d per rank" % (
         info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"], ntiles // world)),
-      "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
-      "gpu_launches": K * (1 + ntiles * info["numOps"]), "clocks": clocks,   # all ranks: autoexposure + every tile's ops
-      "exchange": "CUDA IPC peer mappings of rank 0's frame; peers stage their tile rectangles with copy-engine transfers over "
-                  "NVLink (in: tile + overlap, out: interior); NCCL broadcast(4 B) + all_reduce(4 B) per frame; two frames in flight",
+      "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "frame_on_rank0": on_rank0,
+      # all ranks: per tile the filter's ops + one autoexposure-bins launch, per rank one reduce
+      "gpu_launches": K * (ntiles * (info["numOps"] + 1) + world), "clocks": clocks,
+      "exchange": "every rank holds its tiles' inputs (tile + overlap); autoexposure: per-tile bin kernels + NCCL all-reduce of the "
+                  "bin array (%d B) + fixed-order fold on every rank; output rectangles assembled in rank 0's buffer by copy-engine "
+                  "peer writes over NVLink (CUDA IPC); 4-byte all-reduce joins the frame; two frames in flight" % (4 * sets[0][2].nbins),
     }
     print(json.dumps(line))
-  for _, dev, sf in sets:
-    sf.release()
-    dev.release()
+  host.release()
   dist.barrier()
   dist.destroy_process_group()

@@ -312,3 +312,39 @@ def test_pinned_host_images_zero_copy(device, oracle):
   e, p = metrics(ho.numpy(), ref)
   assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
   f.release()
+
+
+def test_frame_graph_replay_bit_identical():
+  """Device parameter "graph": frames replayed as one CUDA graph equal the eagerly launched frames bit
+  for bit, new image contents are picked up by the replay, and swapping image pointers (what a
+  renderer's double buffering does, core/filter.cpp:52-56: no re-commit) re-captures."""
+  W, H = 1700, 820
+  tza = weights.model_tza("base", 9, seed=0)
+  frames = [synth.benchmark_images(W, H, hdr=True, seed=30 + i) for i in range(2)]
+  outs = {}
+  for graph in (0, 1):
+    dev = api.Device((0,)).commit()
+    dev.set("graph", graph)
+    dev.set("maxTilePixels", 1000 * 1000)  # two tiles per frame
+    t = [{k: torch.from_numpy(v).cuda() for k, v in fr.items()} for fr in frames]
+    o = [torch.zeros((H, W, 3), device="cuda") for _ in range(2)]
+    f = dev.new_filter("RT")
+    f.set("hdr", True); f.set_data("weights", tza)
+    res = []
+    for it in range(6):                    # A A A B B A: eager, capture, replay, eager(B), capture(B), eager(A) ...
+      s = 0 if it in (0, 1, 2, 5) else 1
+      for k, v in t[s].items():
+        f.set_image(k, v)
+      f.set_image("output", o[s])
+      f.commit()
+      if it == 2:                          # same pointers, new pixel values: the replay must read them
+        t[0]["color"].mul_(0.5)
+      f.execute_async()
+      dev.sync()
+      res.append(o[s].cpu().numpy().copy())
+    assert f.info()["tileCountH"] * f.info()["tileCountW"] > 1
+    outs[graph] = res
+    f.release(); dev.release()
+  for a, b in zip(outs[0], outs[1]):
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+  assert not np.array_equal(outs[1][1], outs[1][2])

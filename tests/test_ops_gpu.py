@@ -199,7 +199,7 @@ def test_autoexposure(W, H, dtype, oracle):
   scratch = torch.empty(L.oidnb200_autoexposure_scratch_bytes(H, W), dtype=torch.uint8, device="cuda")
   dst = torch.zeros(1, dtype=torch.float32, device="cuda")
   gi = image_of(t)
-  for _ in range(2):  # second launch checks that the ticket re-arms
+  for _ in range(2):  # relaunch on the same scratch
     check(L.oidnb200_autoexposure_launch(C.byref(gi), scratch.data_ptr(), dst.data_ptr(), torch.cuda.current_stream().cuda_stream))
   got = float(dst.cpu()[0])
   assert np.isfinite(got) and abs(got - ref) <= 2e-5 * abs(ref), (got, ref)
@@ -213,6 +213,49 @@ def test_autoexposure_black_image_gives_one():
   gi = image_of(t)
   check(L.oidnb200_autoexposure_launch(C.byref(gi), scratch.data_ptr(), dst.data_ptr(), torch.cuda.current_stream().cuda_stream))
   assert float(dst.cpu()[0]) == 1.0
+
+
+@pytest.mark.parametrize("W,H", [(130, 70), (1000, 612)])
+def test_autoexposure_bins_by_rectangle_equal_whole_image(W, H):
+  """The multi-GPU decomposition: bins computed rectangle by rectangle into separate zero-filled arrays
+  and summed give bit for bit the array (and the scale) of the single launch. Pixels outside a
+  rectangle's bins are poisoned with NaN-free garbage to show they are not read."""
+  img = synth.benchmark_images(W, H, hdr=True, albedo=False, normal=False, seed=12)["color"]
+  img[H // 2 - 24:H // 2 + 24, : W // 2] = 0.0       # >= 1 whole bin below the 1e-8 threshold (-inf entries)
+  L = capi.lib()
+  st = torch.cuda.current_stream().cuda_stream
+  nbh, nbw = C.c_int(), C.c_int()
+  L.oidnb200_autoexposure_bin_grid(H, W, C.byref(nbh), C.byref(nbw))
+  nbh, nbw = nbh.value, nbw.value
+  assert (nbh, nbw) == ((H + 15) // 16, (W + 15) // 16)
+  t = torch.from_numpy(img).cuda()
+  whole = torch.zeros(nbh * nbw, dtype=torch.float32, device="cuda")
+  ref_scale = torch.zeros(1, device="cuda")
+  check(L.oidnb200_autoexposure_bins_launch(C.byref(image_of(t)), 0, nbh, 0, nbw, whole.data_ptr(), st))
+  check(L.oidnb200_autoexposure_reduce_launch(whole.data_ptr(), nbh * nbw, ref_scale.data_ptr(), st))
+  one = torch.zeros(1, device="cuda")
+  scratch = torch.empty(L.oidnb200_autoexposure_scratch_bytes(H, W), dtype=torch.uint8, device="cuda")
+  check(L.oidnb200_autoexposure_launch(C.byref(image_of(t)), scratch.data_ptr(), one.data_ptr(), st))
+  assert one.cpu().numpy().view(np.uint32)[0] == ref_scale.cpu().numpy().view(np.uint32)[0]
+  total = torch.zeros_like(whole)
+  hs, ws = [0, nbh // 3, nbh], [0, nbw // 2, nbw]
+  for i in range(2):
+    for j in range(2):
+      # this "rank" holds only the pixels of its bins; everything else is garbage
+      h0, h1 = hs[i] * H // nbh, hs[i + 1] * H // nbh
+      w0, w1 = ws[j] * W // nbw, ws[j + 1] * W // nbw
+      local = torch.full_like(t, 1e30)
+      local[h0:h1, w0:w1] = t[h0:h1, w0:w1]
+      part = torch.zeros_like(whole)
+      check(L.oidnb200_autoexposure_bins_launch(C.byref(image_of(local)), hs[i], hs[i + 1], ws[j], ws[j + 1], part.data_ptr(), st))
+      total += part
+  assert np.array_equal(total.cpu().numpy().view(np.uint32), whole.cpu().numpy().view(np.uint32))
+  assert np.isneginf(whole.cpu().numpy()).any()
+  got = torch.zeros(1, device="cuda")
+  check(L.oidnb200_autoexposure_reduce_launch(total.data_ptr(), nbh * nbw, got.data_ptr(), st))
+  assert got.cpu().numpy().view(np.uint32)[0] == ref_scale.cpu().numpy().view(np.uint32)[0]
+  with pytest.raises(RuntimeError):
+    check(L.oidnb200_autoexposure_bins_launch(C.byref(image_of(t)), 0, nbh + 1, 0, nbw, whole.data_ptr(), st))
 
 
 def test_pool_upsample_image_copy(oracle):

@@ -40,6 +40,15 @@ def _worker(rank, world, port, q):
     dist.all_reduce(total)                     # the join: all ranks' rectangles together
     assert int(total.min()) == 1 and int(total.max()) == 1, "ranks' output rectangles must partition the frame"
     out[(H, W, large)] = len(mine)
+    # autoexposure bins: the ranks' bin rectangles partition the bin grid (sharded.bins_of_tile)
+    nbh, nbw = sharded.bin_grid(H, W)
+    bcover = np.zeros((nbh, nbw), np.int32)
+    for t in mine:
+      bh0, bh1, bw0, bw1 = sharded.bins_of_tile(t, H, W)
+      bcover[bh0:bh1, bw0:bw1] += 1
+    btotal = torch.from_numpy(bcover)
+    dist.all_reduce(btotal)
+    assert int(btotal.min()) == 1 and int(btotal.max()) == 1, "ranks' bin rectangles must partition the bin grid"
     # staged exchange (ShardedFilter stage=True) with an identity "filter": a rank copies its input
     # rectangles from the owner's frame into zeroed local staging, produces its interior rectangles
     # from staging only, and copies them back; the joined output must equal the frame.
@@ -56,6 +65,25 @@ def _worker(rank, world, port, q):
       joined = torch.from_numpy(result)
       dist.all_reduce(joined)
       assert np.array_equal(joined.numpy(), frame)
+      # the autoexposure exchange of the distributed frame: every rank fills the bins of its tiles from
+      # its LOCAL pixels into a zero array, the all-reduce (sum) completes it: x + 0 = x exactly
+      def bin_value(img, bi, bj):
+        h0, h1 = bi * H // nbh, (bi + 1) * H // nbh
+        w0, w1 = bj * W // nbw, (bj + 1) * W // nbw
+        return np.float32(img[h0:h1, w0:w1].mean(dtype=np.float64))
+      step = max(1, nbh // 6), max(1, nbw // 8)     # a sample of the grid keeps the test fast
+      mine_bins = np.zeros((nbh, nbw), np.float32)
+      for t in mine:
+        bh0, bh1, bw0, bw1 = sharded.bins_of_tile(t, H, W)
+        for bi in range(bh0, bh1):
+          for bj in range(bw0, bw1):
+            if bi % step[0] == 0 and bj % step[1] == 0:
+              mine_bins[bi, bj] = bin_value(local, bi, bj)
+      allb = torch.from_numpy(mine_bins)
+      dist.all_reduce(allb)
+      for bi in range(0, nbh, step[0]):
+        for bj in range(0, nbw, step[1]):
+          assert allb[bi, bj].item() == bin_value(frame, bi, bj), (bi, bj)
   # handle exchange: rank 0's 64-byte handles reach every rank unchanged
   handles = {"color": bytes(range(64)), "output": bytes(range(64, 128))} if rank == 0 else None
   got = sharded.broadcast_object(dist, handles, 0)

@@ -18,7 +18,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 W, H = 2400, 1700
 tza = weights.model_tza("base", 9, seed=0)
-frame = synth.benchmark_images(W, H, hdr=True, seed=21) if rank == 0 else None
+full = synth.benchmark_images(W, H, hdr=True, seed=21)   # deterministic: every rank generates the same frame
+frame = full if rank == 0 else None
 stream = torch.cuda.Stream()
 ok = True
 with torch.cuda.stream(stream):
@@ -37,11 +38,28 @@ with torch.cuda.stream(stream):
       sf = sf0
     else:
       sf0.release()
+  # distributed frame: every rank holds only its own tiles' source rectangles (the rest of its local
+  # images is garbage), autoexposure by bin all-reduce, output assembled on rank 0 over NVLink
+  sfd = sharded.ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, source="distributed")
+  garbage = np.full((H, W, 3), 1e30, np.float32)
+  for n in sfd.inputs:
+    sfd.local[n].write(garbage)
+  sfd.upload_tiles({n: full[n].ctypes.data for n in sfd.inputs})
+  for _ in range(2):
+    sfd.execute_async()
+  torch.cuda.synchronize(); dist.barrier()
+  if rank == 0:
+    o = np.zeros((H, W, 3), np.float32); sfd.bufs["output"].read(o); outs.append(o)
+  scale_d = float(sfd.scale.cpu()[0])
+  sfd.release()
   info = sf.filter.info()
   if rank == 0:
     got = outs[1]
+    same_d = np.array_equal(outs[2].view(np.uint32), outs[1].view(np.uint32))
+    print("distributed frame == frame on rank 0: %s (autoexposure scale %.9g vs %.9g)" % (same_d, scale_d, float(sf.scale.cpu()[0])))
     ok = np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
     print("staged == direct P2P: %s" % ok)
+    ok = ok and same_d
     # same plan on one GPU: numShards=world keeps the tile grid, but this filter runs every tile
     t = {k: torch.from_numpy(v).cuda() for k, v in frame.items()}
     out = torch.zeros((H, W, 3), device="cuda")
