@@ -6,10 +6,11 @@
 // their CPU twins (devices/cpu/cpu_input_process.isph:31-136, cpu_output_process.isph:29-70,
 // cpu_autoexposure.cpp:22-64). Transfer functions: core/color.h:29-165.
 //
-// These kernels move bytes: each thread owns whole pixels, tensor stores are 16-byte vectors
-// (one pixel of the 16-channel network input is two of them), packed fp32 RGB images are read as
-// float4 triples (4 pixels = 48 B), and the autoexposure is a single pass with warp-shuffle
-// reductions and a last-block-done final reduction instead of three launches.
+// These kernels move bytes: each thread owns whole pixels; on the fast paths a warp owns a span of
+// 128 pixels, moves packed fp32 RGB rows as consecutive 16-byte chunks (staged through shared
+// memory to change ownership from chunks to pixels) and writes a pixel of the 16-channel network
+// input with one 32-byte store; the autoexposure is a bin pass with warp-shuffle reductions plus
+// a fixed-order fold instead of the reference's three launches.
 #include "common.h"
 #include "../../../include/oidn_b200_kernels.h"
 #include <cuda_fp16.h>
@@ -238,48 +239,102 @@ __global__ void __launch_bounds__(256) input_process_kernel(const InputParams p)
 }
 
 // Fast path: packed fp32 RGB images (pixel stride 12 B, 16-B aligned rows), tile origins and
-// widths multiples of 4 pixels. One thread owns 4 consecutive pixels: three float4 loads per
-// image (48 B) and eight 16-B stores.
-__device__ __forceinline__ void load4px(const Img& im, int hs, int ws, float3 (&o)[4])
+// widths multiples of 4 pixels. A warp owns a span of 128 consecutive tile-buffer pixels of one row
+// and moves it with fully coalesced accesses in both directions:
+//   * per image the span is 1536 contiguous bytes = 96 16-byte chunks; lane L loads chunks L, L+32,
+//     L+64 (LDG.128, consecutive lanes -> consecutive addresses) and parks them in the warp's
+//     shared-memory slice;
+//   * lane L then owns pixels L, L+32, L+64, L+96 of the span: it reads their 3 floats back from
+//     shared memory (word stride 3 across lanes: conflict-free), converts, and writes each pixel's
+//     16 fp16 channels with one 32-byte store -- a warp store instruction covers 1 KiB contiguous.
+// Validity is per 4-pixel group (48 B = 3 chunks): a group is either inside the tile or zero.
+constexpr int kSpanPx = 128;                       // pixels per warp span
+constexpr int kSpanBytes = kSpanPx * 12;           // per image
+constexpr int kRowWarps = 8;                       // warps per block = spans per block
+
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint4& lo, const uint4& hi)
 {
-  const float4* q = reinterpret_cast<const float4*>(im.ptr + (size_t)hs * im.rs + (size_t)ws * 12);
-  const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-  o[0] = make_float3(q0.x, q0.y, q0.z);
-  o[1] = make_float3(q0.w, q1.x, q1.y);
-  o[2] = make_float3(q1.z, q1.w, q2.x);
-  o[3] = make_float3(q2.y, q2.z, q2.w);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(ptr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
 }
 
-__global__ void __launch_bounds__(256) input_process_vec4_kernel(const InputParams p)
+// chunks L, L+32, L+64 of the span's bytes of one image row (zeros outside the valid groups)
+__device__ __forceinline__ void span_ldg(const Img& im, bool present, int hs, int ws0, int lane, int g_lo, int g_hi,
+                                         float4 (&q)[3])
 {
-  const int wd = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int hd = blockIdx.y;
-  if (wd >= p.TW) return;
-  const int h = hd - p.tile.hDstBegin, w = wd - p.tile.wDstBegin;
-  uint4* d = reinterpret_cast<uint4*>(p.dst + ((size_t)hd * p.TW + wd) * 16);
-  if (h >= 0 && h < p.tile.H && w >= 0 && w < p.tile.W) // all four pixels inside (W, wDstBegin multiples of 4)
-  {
-    const int hs = h + p.tile.hSrcBegin, ws = w + p.tile.wSrcBegin;
-    const float scale = p.tf.input_scale_ptr ? *p.tf.input_scale_ptr : p.tf.input_scale;
-    const bool has_a = p.albedo.ptr != nullptr, has_n = has_a && p.normal.ptr != nullptr;
-    float3 c[4], a[4], n[4];
-    load4px(p.input, hs, ws, c);
-    if (has_a) load4px(p.albedo, hs, ws, a);
-    if (has_n) load4px(p.normal, hs, ws, n);
+  const uint8_t* row = im.ptr + (size_t)hs * im.rs + (long long)ws0 * 12; // ws0 may be negative: only valid groups are touched
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-      uint4 lo, hi;
-      input_pixel(p, scale, c[i], a[i], n[i], has_a, has_n, lo, hi);
-      d[2 * i] = lo;
-      d[2 * i + 1] = hi;
-    }
+  for (int i = 0; i < 3; ++i)
+  {
+    const int c = i * 32 + lane;
+    const int g = c / 3;
+    q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (present && g >= g_lo && g < g_hi) q[i] = __ldg(reinterpret_cast<const float4*>(row + (size_t)c * 16));
   }
-  else
+}
+
+__device__ __forceinline__ void span_sts(float* slice, int lane, const float4 (&q)[3])
+{
+#pragma unroll
+  for (int i = 0; i < 3; ++i) reinterpret_cast<float4*>(slice)[i * 32 + lane] = q[i];
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) input_process_rows_kernel(const InputParams p)
+{
+  __shared__ __align__(16) float stage[kRowWarps][3][kSpanBytes / 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wd0 = (blockIdx.x * kRowWarps + warp) * kSpanPx;   // first tile-buffer pixel of the span
+  const int hd = blockIdx.y;
+  if (wd0 >= p.TW) return;
+  const int h = hd - p.tile.hDstBegin;
+  __half* drow = p.dst + ((size_t)hd * p.TW + wd0) * 16;
+  const int npx = min(kSpanPx, p.TW - wd0);                     // multiple of 4
+  // 4-pixel groups of the span that lie inside the tile: [g_lo, g_hi)
+  int g_lo = 0, g_hi = 0;
+  if (h >= 0 && h < p.tile.H)
+  {
+    g_lo = max(0, (p.tile.wDstBegin - wd0) >> 2);
+    g_hi = min(npx >> 2, (p.tile.wDstBegin + p.tile.W - wd0) >> 2);
+  }
+  if (g_hi <= g_lo)
   {
     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = z;
+    for (int j = 0; j < 4; ++j)
+      if (j * 32 + lane < npx) st_global_v8(drow + (size_t)(j * 32 + lane) * 16, z, z);
+    return;
+  }
+  const int hs = h + p.tile.hSrcBegin;
+  const int ws0 = wd0 - p.tile.wDstBegin + p.tile.wSrcBegin;   // image column of the span's first pixel
+  const bool has_a = p.albedo.ptr != nullptr, has_n = has_a && p.normal.ptr != nullptr;
+  // all nine 16-byte loads are in flight before the first one is consumed
+  float4 qc[3], qa[3], qn[3];
+  span_ldg(p.input, true, hs, ws0, lane, g_lo, g_hi, qc);
+  span_ldg(p.albedo, has_a, hs, ws0, lane, g_lo, g_hi, qa);
+  span_ldg(p.normal, has_n, hs, ws0, lane, g_lo, g_hi, qn);
+  const float scale = p.tf.input_scale_ptr ? *p.tf.input_scale_ptr : p.tf.input_scale;
+  asm volatile("" ::: "memory"); // keep the compiler from sinking loads between the shared-memory stores
+  span_sts(stage[warp][0], lane, qc);
+  span_sts(stage[warp][1], lane, qa);
+  span_sts(stage[warp][2], lane, qn);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+  {
+    const int px = j * 32 + lane;
+    if (px >= npx) continue;
+    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+    const int g = px >> 2;
+    if (g >= g_lo && g < g_hi)
+    {
+      const float* c = &stage[warp][0][px * 3];
+      const float* qa3 = &stage[warp][1][px * 3];
+      const float* qn3 = &stage[warp][2][px * 3];
+      const float3 a = make_float3(qa3[0], qa3[1], qa3[2]), n = make_float3(qn3[0], qn3[1], qn3[2]);
+      input_pixel(p, scale, make_float3(c[0], c[1], c[2]), a, n, has_a, has_n, lo, hi);
+    }
+    st_global_v8(drow + (size_t)px * 16, lo, hi);
   }
 }
 
@@ -341,28 +396,48 @@ __global__ void __launch_bounds__(256) output_process_kernel(const OutputParams 
   img_set3(p.dst, h + p.tile.hDstBegin, w + p.tile.wDstBegin, v);
 }
 
-// Packed fp32 RGB destination, tile origin/width multiples of 4 pixels: 4 pixels per thread,
-// three float4 stores.
-__global__ void __launch_bounds__(256) output_process_vec4_kernel(const OutputParams p)
+// Packed fp32 RGB destination, tile origin/width multiples of 4 pixels. The mirror image of the
+// input fast path: a warp owns 128 consecutive pixels of one tile row; lane L converts pixels L,
+// L+32, L+64, L+96 (8-byte loads at the tensor's 32-byte pixel pitch: 8 lines per warp load instead
+// of 32), parks the 3 floats in the warp's shared-memory slice (word stride 3: conflict-free) and
+// the warp writes the span's 1536 bytes as 96 consecutive 16-byte chunks.
+__global__ void __launch_bounds__(kRowWarps * 32) output_process_rows_kernel(const OutputParams p)
 {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  __shared__ __align__(16) float stage[kRowWarps][kSpanBytes / 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w0 = (blockIdx.x * kRowWarps + warp) * kSpanPx;    // first tile pixel of the span
   const int h = blockIdx.y;
-  if (w >= p.tile.W) return;
+  if (w0 >= p.tile.W) return;
+  const int npx = min(kSpanPx, p.tile.W - w0);                  // multiple of 4
   const float oscale = output_scale(p.tf);
-  const __half* s = p.src + ((size_t)(h + p.tile.hSrcBegin) * p.TW + (w + p.tile.wSrcBegin)) * p.C;
-  float3 v[4];
+  const __half* s = p.src + ((size_t)(h + p.tile.hSrcBegin) * p.TW + (w0 + p.tile.wSrcBegin)) * p.C;
+  uint2 raw[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int j = 0; j < 4; ++j)
   {
-    const uint2 raw = *reinterpret_cast<const uint2*>(s + (size_t)i * p.C);
-    const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
-    v[i] = output_pixel(p, oscale, __low2float(h01), __high2float(h01), __low2float(h23));
+    const int px = j * 32 + lane;
+    raw[j] = make_uint2(0, 0);
+    if (px < npx) raw[j] = *reinterpret_cast<const uint2*>(s + (size_t)px * p.C); // channels 0..3
   }
-  float4* d = reinterpret_cast<float4*>(p.dst.ptr + (size_t)(h + p.tile.hDstBegin) * p.dst.rs +
-                                        (size_t)(w + p.tile.wDstBegin) * 12);
-  d[0] = make_float4(v[0].x, v[0].y, v[0].z, v[1].x);
-  d[1] = make_float4(v[1].y, v[1].z, v[2].x, v[2].y);
-  d[2] = make_float4(v[2].z, v[3].x, v[3].y, v[3].z);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+  {
+    const int px = j * 32 + lane;
+    if (px >= npx) continue;
+    const __half2 h01 = *reinterpret_cast<const __half2*>(&raw[j].x), h23 = *reinterpret_cast<const __half2*>(&raw[j].y);
+    const float3 v = output_pixel(p, oscale, __low2float(h01), __high2float(h01), __low2float(h23));
+    float* q = &stage[warp][px * 3];
+    q[0] = v.x; q[1] = v.y; q[2] = v.z;
+  }
+  __syncwarp();
+  uint8_t* d = p.dst.ptr + (size_t)(h + p.tile.hDstBegin) * p.dst.rs + (size_t)(w0 + p.tile.wDstBegin) * 12;
+  const int nchunks = npx * 3 / 4;                              // 16-byte chunks of the span
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    const int c = i * 32 + lane;
+    if (c < nchunks) reinterpret_cast<float4*>(d)[c] = reinterpret_cast<const float4*>(stage[warp])[c];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,14 +475,21 @@ __global__ void __launch_bounds__(kAeThreads) autoexposure_bins_kernel(const AeB
     const int w0 = (int)((long long)bj * p.src.W / p.nbw), w1 = (int)((long long)(bj + 1) * p.src.W / p.nbw);
     float L = 0.f;
     const int w = w0 + col;
-    if (w < w1)
-      for (int h = h0 + rpar; h < h1; h += 2)
-      {
-        const float3 c = img_get3(p.src, h, w);
-        const float r = clampf(nan_to_zero(c.x), 0.f, FLT_MAX), g = clampf(nan_to_zero(c.y), 0.f, FLT_MAX),
-                    b = clampf(nan_to_zero(c.z), 0.f, FLT_MAX);
-        L += 0.212671f * r + 0.715160f * g + 0.072169f * b; // core/color.h:169-172
-      }
+    // a bin has at most 16 rows = 8 per lane half: all 8 row loads are issued before the first use
+    float3 c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      const int h = h0 + rpar + 2 * k;
+      c[k] = (w < w1 && h < h1) ? img_get3(p.src, h, w) : make_float3(0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      const float r = clampf(nan_to_zero(c[k].x), 0.f, FLT_MAX), g = clampf(nan_to_zero(c[k].y), 0.f, FLT_MAX),
+                  b = clampf(nan_to_zero(c[k].z), 0.f, FLT_MAX);
+      L += 0.212671f * r + 0.715160f * g + 0.072169f * b; // core/color.h:169-172
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
     L /= (float)((h1 - h0) * (w1 - w0));
@@ -557,9 +639,8 @@ int oidnb200_input_process_launch(const oidnb200_image* color, const oidnb200_im
                    tile->W % 4 == 0 && tile->wDstBegin % 4 == 0 && tile->wSrcBegin % 4 == 0;
   if (vec)
   {
-    const int threads = 128;
-    dim3 grid((TW / 4 + threads - 1) / threads, TH);
-    input_process_vec4_kernel<<<grid, threads, 0, st>>>(p);
+    dim3 grid((TW + kSpanPx * kRowWarps - 1) / (kSpanPx * kRowWarps), TH);
+    input_process_rows_kernel<<<grid, kRowWarps * 32, 0, st>>>(p);
   }
   else
   {
@@ -594,9 +675,8 @@ int oidnb200_output_process_launch(const void* src, int TH, int TW, int C, const
   const bool vec = packed_rgb32(p.dst) && tile->W % 4 == 0 && tile->wDstBegin % 4 == 0;
   if (vec)
   {
-    const int threads = 128;
-    dim3 grid((tile->W / 4 + threads - 1) / threads, tile->H);
-    output_process_vec4_kernel<<<grid, threads, 0, st>>>(p);
+    dim3 grid((tile->W + kSpanPx * kRowWarps - 1) / (kSpanPx * kRowWarps), tile->H);
+    output_process_rows_kernel<<<grid, kRowWarps * 32, 0, st>>>(p);
   }
   else
   {
