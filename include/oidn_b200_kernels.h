@@ -151,6 +151,19 @@ OIDNB200_API int oidnb200_output_process_launch(const void* src, int TH, int TW,
                                                 int hdr, int snorm, const oidnb200_image* dst,
                                                 oidnb200_stream stream);
 
+/* OutputProcess fused into the network's last convolution (the reference runs the two ops back to
+ * back: core/unet_filter.cpp:495-496 + :228-231). After this call oidnb200_conv_launch applies the
+ * output process (devices/gpu/gpu_output_process.h:35-73; same tile / transfer / hdr / snorm meaning as
+ * oidnb200_output_process_launch above) to channels 0..2 of its result and writes the tile rectangle
+ * straight into `dst`; the conv's tensor `dst` is then NOT written. The result is bit-identical to
+ * conv + oidnb200_output_process_launch. Supported for a conv with 16 padded output channels and no
+ * post-op, and a FLOAT3 image with pixel stride 12: otherwise OIDNB200_ERR_UNSUPPORTED is returned and
+ * the conv stays unfused (the caller then launches the separate pass). dst == NULL removes the
+ * fusion. Cheap: call per tile per frame like OutputProcess::setTile/setDst (no tensor-map encode). */
+OIDNB200_API int oidnb200_conv_set_output_process(oidnb200_conv* conv, const oidnb200_tile* tile,
+                                                  const oidnb200_transfer* tf, int hdr, int snorm,
+                                                  const oidnb200_image* dst);
+
 /* Autoexposure (core/autoexposure.h:14-53, devices/gpu/gpu_autoexposure.h:13-164; the reference
  * uses three launches): result = 0.18 / exp2(mean log2 of the bin luminances > 1e-8) (1 if none)
  * stored to *dst (device float). Bins are <= 16x16 pixels, bin i covers rows [i*H/nbh, (i+1)*H/nbh).

@@ -65,6 +65,8 @@ KERNEL_ABI = {
   "oidnb200_conv_pack_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
   "oidnb200_conv_bind": (C.c_int, [C.c_void_p] * 6),
   "oidnb200_conv_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "oidnb200_conv_set_output_process": (C.c_int, [C.c_void_p, C.POINTER(Tile), C.POINTER(Transfer), C.c_int, C.c_int,
+                                                 C.POINTER(Image)]),
   "oidnb200_conv_launch_simt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
   "oidnb200_conv_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
   "oidnb200_conv_get_info": (C.c_int, [C.c_void_p, C.POINTER(ConvInfo)]),

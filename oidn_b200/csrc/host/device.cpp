@@ -120,6 +120,7 @@ void Device::setInt(const std::string& name, int value)
   else if (name == "profile") profile = value; // backend specific: per-op CUDA-event timing
   else if (name == "maxTilePixels") maxTilePixels = value; // backend specific
   else if (name == "graph") graph = value;                 // backend specific: 1 = replay frames as a CUDA graph (frame streams)
+  else if (name == "fuseOutput") fuseOutput = value;       // backend specific: 1 = output process inside the last conv's epilogue
   else if (name == "tilePolicy") tilePolicy = value;       // backend specific: 0 = reference search, 1 = fewest recomputed pixels
   else if (committed) throw Exception(Error::InvalidOperation, "device can be committed only once");
   else throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
@@ -138,6 +139,7 @@ int Device::getInt(const std::string& name) const
   if (name == "maxTilePixels") return (int)maxTilePixels;
   if (name == "tilePolicy") return tilePolicy;
   if (name == "graph") return graph;
+  if (name == "fuseOutput") return fuseOutput;
   if (name == "systemMemorySupported" || name == "managedMemorySupported")
   {
     int v = 0;

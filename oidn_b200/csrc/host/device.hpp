@@ -65,6 +65,7 @@ private:
   int profile = 0;
   long maxTilePixels;
   int tilePolicy = 1;
+  int fuseOutput = 1;
   int graph = 0;
   std::string weightsDir;
   std::mutex mutex;

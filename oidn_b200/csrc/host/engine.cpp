@@ -199,6 +199,20 @@ void OutputProcess::submitKernels()
                                           engine->getStream()), "output process");
 }
 
+bool OutputProcess::fuseInto(Conv& producer, bool on)
+{
+  if (on)
+  {
+    const oidnb200_image d = abiImage(dst);
+    const oidnb200_transfer tf = transferFunc->abi();
+    const int rc = oidnb200_conv_set_output_process(producer.getHandle(), &tile, &tf, hdr, snorm, &d);
+    if (rc == 0) return true;
+    if (rc != OIDNB200_ERR_UNSUPPORTED) checkABI(rc, "fused output process");
+  }
+  oidnb200_conv_set_output_process(producer.getHandle(), nullptr, nullptr, 0, 0, nullptr);
+  return false;
+}
+
 void Autoexposure::setSrc(const Image& image)
 {
   if (!image || image.W != W || image.H != H) throw std::invalid_argument("invalid autoexposure source");

@@ -83,6 +83,7 @@ public:
   void finalize() override;      // encodes the TMA tensor maps
   void submitKernels() override;
   oidnb200_conv_info getInfo() const;
+  oidnb200_conv* getHandle() const { return handle; }
 
 private:
   Engine* engine;
@@ -142,6 +143,11 @@ public:
   void setDst(const Image& image) { dst = image; }
   void setTile(int hSrc, int wSrc, int hDst, int wDst, int H, int W) { tile = oidnb200_tile{hSrc, wSrc, hDst, wDst, H, W}; }
   void submitKernels() override;
+  // Folds this op (current tile, destination, transfer function) into the epilogue of the conv that
+  // produces its source, or removes the fusion (on = false). Returns false when the kernel ABI does
+  // not support the combination (image format): the conv is then left unfused and this op must be
+  // submitted as a pass of its own.
+  bool fuseInto(Conv& producer, bool on);
 private:
   Engine* engine; TensorDesc srcDesc; std::shared_ptr<TransferFunction> transferFunc; bool hdr, snorm;
   const void* src = nullptr; Image dst; oidnb200_tile tile{};

@@ -303,6 +303,7 @@ std::vector<uint64_t> UNetFilter::frameKey() const
   k.push_back(bits);
   k.push_back((uint64_t)(uintptr_t)inputScaleDevPtr);
   k.push_back(((uint64_t)(uint32_t)numShards << 32) | (uint32_t)shardIndex);
+  k.push_back((uint64_t)device->getInt("fuseOutput"));
   return k;
 }
 
@@ -652,6 +653,7 @@ void UNetFilter::execute(SyncMode sync)
       checkCancel();
       Instance& inst = instances[tileIndex % numEngines];
       inst.graph->setProfiling(profiling);
+      inst.graph->setFuseOutput(device->getInt("fuseOutput") != 0);
       inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
       inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
       inst.graph->submit();

@@ -13,7 +13,7 @@ Graph::~Graph() { clear(); }
 void Graph::clear()
 {
   ops.clear(); nodes.clear(); convs.clear();
-  inputProcess.reset(); outputProcess.reset();
+  inputProcess.reset(); outputProcess.reset(); outputConv.reset();
   inputNode = outputSrcNode = -1;
   planner.clear();
   planned = finalized = false;
@@ -61,6 +61,7 @@ void Graph::addOutputProcess(const std::string& name, Value src, const std::shar
   ops.push_back(outputProcess);
   planner.addDep(opID, n.allocID);
   outputSrcNode = src.id;
+  outputConv = std::dynamic_pointer_cast<Conv>(ops.at(n.opID));
 }
 
 Graph::Value Graph::addConv(const std::string& name, Value src, Activation activation, PostOp postOp)
@@ -194,14 +195,19 @@ void Graph::submit()
 {
   if (!finalized) throw std::logic_error("graph not finalized");
   engine->makeCurrent();
+  // The output process runs inside the last conv's epilogue when the kernel supports the frame's
+  // output image; otherwise (or with fuseOutput off) it is the separate pass of the reference.
+  const bool fused = outputProcess && outputConv && outputProcess->fuseInto(*outputConv, fuseOutput);
   if (!profiling)
   {
-    for (auto& op : ops) op->submit();
+    for (auto& op : ops)
+      if (!(fused && op == outputProcess)) op->submit();
     return;
   }
   cudaStream_t st = static_cast<cudaStream_t>(engine->getStream());
   for (size_t i = 0; i < ops.size(); ++i)
   {
+    if (fused && ops[i] == outputProcess) continue;
     cudaEvent_t e0, e1;
     checkCuda(cudaEventCreate(&e0), "cudaEventCreate");
     checkCuda(cudaEventCreate(&e1), "cudaEventCreate");

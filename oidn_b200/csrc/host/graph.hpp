@@ -45,6 +45,9 @@ public:
   // stream and adds the elapsed times to `out` (one entry per op, in op order).
   struct OpTime { std::string name; int kind; double ms; int launches; };
   void setProfiling(bool on) { profiling = on; }
+  // Output process folded into the last conv's epilogue when the output image allows it (default on;
+  // device parameter "fuseOutput"). Decided per submit(): it depends on the image set for the frame.
+  void setFuseOutput(bool on) { fuseOutput = on; }
   void collectProfile(std::vector<OpTime>& out);
 
   const std::shared_ptr<InputProcess>& getInputProcess() const { return inputProcess; }
@@ -83,6 +86,8 @@ private:
   std::shared_ptr<InputProcess> inputProcess;
   std::shared_ptr<OutputProcess> outputProcess;
   int inputNode = -1, outputSrcNode = -1;
+  std::shared_ptr<Conv> outputConv;   // producer of the output process's source, if it is a conv
+  bool fuseOutput = true;
   ArenaPlanner planner;
   bool planned = false, finalized = false;
   size_t privateByteSize = 0;

@@ -46,6 +46,23 @@ __host__ __device__ constexpr uint32_t out_piece_off(int nb, int i, int rows)
 
 enum PostOp : int { POST_NONE = 0, POST_POOL = 1, POST_UPSAMPLE = 2 /* SIMT witness only */ };
 
+// Output process fused into the epilogue of the network's last convolution (16 padded output
+// channels, 3 used): instead of storing the tensor, every pixel of the tile's output rectangle goes
+// through the output-process math (devices/gpu/gpu_output_process.h:35-73) and is written to the
+// packed fp32 RGB output image. Removes the tensor write, its re-read and one launch.
+struct FusedOutput
+{
+  int      enabled;
+  unsigned char* ptr;               // output image: 3 x fp32 per pixel, pixel stride 12 bytes
+  long long rs;                     // row stride in bytes
+  int      hSrc, wSrc, hDst, wDst, H, W; // core/tile.h: rectangle in the tensor -> origin in the image
+  int      tf_type;                 // OIDNB200_TF_*
+  float    norm, rcp_norm;          // PU / Log normalisation
+  float    input_scale;             // used when input_scale_ptr == nullptr
+  const float* input_scale_ptr;     // autoexposure result (device memory)
+  int      hdr, snorm;
+};
+
 struct ConvKernelParams
 {
   CUtensorMap amap[kMaxChunks]; // activations, one per K chunk (3D, or 4D with a stride-0 dup axis for a virtually upsampled source)
@@ -83,6 +100,7 @@ struct ConvKernelParams
   int      relu, post_op;
   const float* bias;                // fp32 [CoutAlloc]
   unsigned long long* trace;        // [12 warps][16 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
+  FusedOutput fo;                   // fo.enabled: the epilogue writes the output image instead of the tensor
 };
 
 } // namespace oidnb200

@@ -3,6 +3,7 @@
 // of the same op that the GPU tests use as a second witness.
 #include "conv_common.h"
 #include "common.h"
+#include "transfer.cuh"
 #include "../../../include/oidn_b200_kernels.h"
 #include <cuda_fp16.h>
 #include <algorithm>
@@ -509,6 +510,52 @@ int oidnb200_conv_bind(oidnb200_conv* conv, const void* src1, const void* src2, 
                        const void* bias, void* dst)
 {
   return plan_bind(conv->plan, src1, src2, weights, bias, dst);
+}
+
+int oidnb200_conv_set_output_process(oidnb200_conv* conv, const oidnb200_tile* tile, const oidnb200_transfer* tf,
+                                     int hdr, int snorm, const oidnb200_image* dst)
+{
+  ConvPlan& pl = conv->plan;
+  FusedOutput& fo = pl.kp.fo;
+  if (!dst)
+  {
+    fo.enabled = 0;
+    return 0;
+  }
+  const oidnb200_conv_desc& d = pl.desc;
+  Transfer t;
+  if (!tile || !make_transfer(tf, t))
+  {
+    set_error("conv_set_output_process: bad arguments");
+    return OIDNB200_ERR_INVALID;
+  }
+  if (d.Cout != 16 || d.post_op != POST_NONE || pl.kp.ngroups != 1)
+  {
+    set_error("conv_set_output_process: only the last convolution (16 padded output channels, no post-op) can be fused");
+    return OIDNB200_ERR_UNSUPPORTED;
+  }
+  if (dst->format != OIDNB200_FORMAT_FLOAT3 || dst->pixel_stride != 12 || dst->row_stride % 4 != 0 ||
+      reinterpret_cast<uintptr_t>(dst->ptr) % 4 != 0 || !dst->ptr)
+  {
+    set_error("conv_set_output_process: the fused path writes packed fp32 RGB images only");
+    return OIDNB200_ERR_UNSUPPORTED;
+  }
+  if (tile->H < 0 || tile->W < 0 || tile->hSrcBegin < 0 || tile->wSrcBegin < 0 || tile->hSrcBegin + tile->H > d.H ||
+      tile->wSrcBegin + tile->W > d.W || tile->hDstBegin < 0 || tile->wDstBegin < 0 ||
+      tile->hDstBegin + tile->H > dst->H || tile->wDstBegin + tile->W > dst->W)
+  {
+    set_error("conv_set_output_process: tile outside the tensor or the image");
+    return OIDNB200_ERR_INVALID;
+  }
+  fo.enabled = 1;
+  fo.ptr = static_cast<unsigned char*>(dst->ptr);
+  fo.rs = (long long)dst->row_stride;
+  fo.hSrc = tile->hSrcBegin; fo.wSrc = tile->wSrcBegin; fo.hDst = tile->hDstBegin; fo.wDst = tile->wDstBegin;
+  fo.H = tile->H; fo.W = tile->W;
+  fo.tf_type = t.type; fo.norm = t.norm; fo.rcp_norm = t.rcp_norm;
+  fo.input_scale = t.input_scale; fo.input_scale_ptr = t.input_scale_ptr;
+  fo.hdr = hdr; fo.snorm = snorm;
+  return 0;
 }
 
 int oidnb200_conv_launch(const oidnb200_conv* conv, oidnb200_stream stream)

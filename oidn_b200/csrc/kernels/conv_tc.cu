@@ -32,6 +32,7 @@
 // 4-7 = epilogue warpgroup 0, 8-11 = epilogue warpgroup 1.
 #include "conv_common.h"
 #include "ptx.cuh"
+#include "transfer.cuh"
 #include <cuda_fp16.h>
 
 namespace oidnb200 {
@@ -345,6 +346,86 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
   __syncwarp();
 }
 
+
+// Epilogue of the network's last convolution with the output process fused in (p.fo.enabled;
+// CoutG = 16, no pooling): same accumulator hand-off as epilogue<1, false>, but a thread reads only
+// channels 0..3 of its pixel, rounds them to fp16 exactly as the stored tensor would have been
+// (so the result is bit-identical to conv + separate output process), applies the output-process
+// math and writes the pixel's 3 floats to the image. Consecutive lanes write consecutive 12-byte
+// pixels: a warp store covers 384 contiguous bytes. No staging, no TMA store.
+__device__ __forceinline__ void epilogue_fused_output(const ConvKernelParams& p, const EpiCtx& ec TRACE_PARAMS)
+{
+  constexpr int CoutG = 16;
+  const int warp = ec.warp, lane = ec.lane;
+  const int NST  = p.nstreams;
+  const int R    = p.R;
+  const int wg   = (warp - 4) >> 2;
+  const int st   = (NST == 2) ? wg : 0;
+  const bool alternate = (NST == 1);
+  const int vcta = ec.cta * NST + st, nv = ec.nctas * NST;
+  const int nitems = p.nstrips * p.nrowchunks;
+  const int q    = warp & 3;
+  const bool relu = p.relu != 0;
+  const uint32_t tfull  = ec.sbase + SmemLayout::tmem_full + 8 * st * kMaxSlots;
+  const uint32_t tempty = ec.sbase + SmemLayout::tmem_empty + 8 * st * kMaxSlots;
+  const uint32_t lane_base = ec.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)st * (uint32_t)R * CoutG;
+  const float* bias_s = reinterpret_cast<const float*>(ec.sgen + SmemLayout::bias);
+  const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
+
+  const FusedOutput& fo = p.fo;
+  Transfer tf;
+  tf.type = fo.tf_type; tf.norm = fo.norm; tf.rcp_norm = fo.rcp_norm;
+  tf.input_scale = fo.input_scale; tf.input_scale_ptr = fo.input_scale_ptr;
+  // The scale may be the autoexposure result written by an earlier grid of the stream: order this
+  // grid's first read of it after the prerequisite grids (programmatic dependent launch).
+  pdl_wait();
+  const float oscale = output_scale(tf);
+  const bool hdr = fo.hdr != 0, snorm = fo.snorm != 0;
+
+  uint32_t a_mod = 0, a_par = 0;
+  uint32_t rown = 0;
+  for (int item = vcta; item < nitems; item += nv)
+  {
+    const Item it = get_item(p, item);
+    const int x  = it.x0 + q * 32 + lane;                 // this thread's pixel column in the tensor
+    const int xi = x - fo.wSrc;                           // column inside the output rectangle
+    const bool xok = x < p.W && xi >= 0 && xi < fo.W;
+    uint32_t y_mod = a_mod, y_par = a_par;
+    for (int y = it.y0; y <= it.y1; ++y, ++rown)
+    {
+      const uint32_t slot0 = (R - 1) - y_mod;
+      const uint32_t par0 = y_par;
+      if (++y_mod == (uint32_t)R) { y_mod = 0; y_par ^= 1; }
+      if (alternate && (int)(rown & 1) != wg) continue;
+
+      MBAR_WAIT(tfull + 8 * slot0, par0, 5);
+      tc_fence_after();
+      uint32_t v[4];
+      tmem_ld4(lane_base + slot0 * CoutG, v);
+      tmem_ld_wait();
+      // the accumulator slot goes back to the MMA issuer before the (long) per-pixel math
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + 8 * slot0);
+
+      const int yi = y - fo.hSrc;
+      if (xok && yi >= 0 && yi < fo.H)
+      {
+        const float s0 = __uint_as_float(v[0]) + b0, s1 = __uint_as_float(v[1]) + b1, s2 = __uint_as_float(v[2]) + b2;
+        const uint32_t h01 = relu ? pack_half2_relu(s0, s1) : pack_half2(s0, s1);
+        const uint32_t h2x = relu ? pack_half2_relu(s2, 0.f) : pack_half2(s2, 0.f);
+        const __half2 q01 = *reinterpret_cast<const __half2*>(&h01), q2x = *reinterpret_cast<const __half2*>(&h2x);
+        const float3 o = output_pixel(tf, hdr, snorm, false, oscale, __low2float(q01), __high2float(q01), __low2float(q2x));
+        float* d = reinterpret_cast<float*>(fo.ptr + (long long)(yi + fo.hDst) * fo.rs) + (size_t)(xi + fo.wDst) * 3;
+        d[0] = o.x; d[1] = o.y; d[2] = o.z;
+      }
+    }
+    const uint32_t tot = a_mod + (uint32_t)(it.y1 - it.y0 + 1);
+    a_par ^= (tot / R) & 1;
+    a_mod = tot % R;
+  }
+}
+
 } // namespace
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -615,6 +696,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
     EpiCtx ec;
     ec.sbase = sbase; ec.tmem_base = tmem_base; ec.b_region = b_region; ec.sgen = sgen;
     ec.warp = warp; ec.lane = lane; ec.group = group; ec.cta = cta; ec.nctas = nctas;
+    if (p.fo.enabled)
+      epilogue_fused_output(p, ec TRACE_ARGS);
+    else
     switch ((p.CoutG >> 4) * 2 + (p.post_op == POST_POOL ? 1 : 0))
     {
 #define EPI_CASE(NB) case (NB) * 2: epilogue<NB, false>(p, ec TRACE_ARGS); break; case (NB) * 2 + 1: epilogue<NB, true>(p, ec TRACE_ARGS); break;

@@ -12,7 +12,7 @@
 // input with one 32-byte store; the autoexposure is a bin pass with warp-shuffle reductions plus
 // a fixed-order fold instead of the reference's three launches.
 #include "common.h"
-#include "../../../include/oidn_b200_kernels.h"
+#include "transfer.cuh"
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cfloat>
@@ -91,83 +91,6 @@ __device__ __forceinline__ void img_set3(const Img& im, int h, int w, float3 v)
     if (im.C == 3) p[2] = v.z;
   }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Transfer function (core/color.h:29-165)
-// ------------------------------------------------------------------------------------------------
-struct Transfer
-{
-  int type;
-  float norm, rcp_norm;
-  float input_scale;
-  const float* input_scale_ptr;
-};
-
-constexpr float kSrgbA = 12.92f, kSrgbB = 1.055f, kSrgbC = 1.f / 2.4f, kSrgbD = -0.055f;
-constexpr float kSrgbY0 = 0.0031308f, kSrgbX0 = 0.04045f;
-constexpr float kPuA = 1.41283765e+03f, kPuB = 1.64593172e+00f, kPuC = 4.31384981e-01f;
-constexpr float kPuD = -2.94139609e-03f, kPuE = 1.92653254e-01f, kPuF = 6.26026094e-03f;
-constexpr float kPuG = 9.98620152e-01f, kPuY0 = 1.57945760e-06f, kPuY1 = 3.22087631e-02f;
-constexpr float kPuX0 = 2.23151711e-03f, kPuX1 = 3.70974749e-01f;
-
-__host__ __device__ inline float tf_raw_forward(int type, float y)
-{
-  switch (type)
-  {
-  case OIDNB200_TF_SRGB:
-    return y <= kSrgbY0 ? kSrgbA * y : kSrgbB * powf(y, kSrgbC) + kSrgbD;
-  case OIDNB200_TF_PU:
-    if (y <= kPuY0) return kPuA * y;
-    if (y <= kPuY1) return kPuB * powf(y, kPuC) + kPuD;
-    return kPuE * logf(y + kPuF) + kPuG;
-  case OIDNB200_TF_LOG:
-    return logf(y + 1.f);
-  default:
-    return y;
-  }
-}
-
-__device__ __forceinline__ float tf_forward(const Transfer& t, float y)
-{
-  const float x = tf_raw_forward(t.type, y);
-  return (t.type == OIDNB200_TF_PU || t.type == OIDNB200_TF_LOG) ? x * t.norm : x;
-}
-
-__device__ __forceinline__ float tf_inverse(const Transfer& t, float x)
-{
-  switch (t.type)
-  {
-  case OIDNB200_TF_SRGB:
-    return x <= kSrgbX0 ? x / kSrgbA : powf((x - kSrgbD) / kSrgbB, 1.f / kSrgbC);
-  case OIDNB200_TF_PU:
-  {
-    const float u = x * t.rcp_norm;
-    if (u <= kPuX0) return u / kPuA;
-    if (u <= kPuX1) return powf((u - kPuD) / kPuB, 1.f / kPuC);
-    return expf((u - kPuG) / kPuE) - kPuF;
-  }
-  case OIDNB200_TF_LOG:
-    return expf(x * t.rcp_norm) - 1.f;
-  default:
-    return x;
-  }
-}
-
-bool make_transfer(const oidnb200_transfer* tf, Transfer& t)
-{
-  if (!tf || tf->type < OIDNB200_TF_LINEAR || tf->type > OIDNB200_TF_LOG) return false;
-  t.type = tf->type;
-  // core/color.cpp:9-16: normScale = 1/forward(yMax), evaluated on the host in fp32
-  const float xmax = tf_raw_forward(tf->type, 65504.f);
-  t.norm = (float)(1. / xmax);
-  t.rcp_norm = xmax;
-  t.input_scale = tf->input_scale;
-  t.input_scale_ptr = tf->input_scale_ptr;
-  return true;
-}
-
-__device__ __forceinline__ float nan_to_zero(float x) { return isnan(x) ? 0.f : x; }
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b)
 {
@@ -357,33 +280,6 @@ struct OutputParams
   Img dst;
 };
 
-__device__ __forceinline__ float3 output_pixel(const OutputParams& p, float oscale, float x, float y, float z)
-{
-  float v[3] = {x, y, z};
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    v[k] = tf_inverse(p.tf, clampf(nan_to_zero(v[k]), 0.f, FLT_MAX));
-  if (p.dst.C == 1)
-  {
-    const float m = (v[0] + v[1] + v[2]) * (1.f / 3.f);
-    v[0] = v[1] = v[2] = m;
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-  {
-    if (p.snorm) v[k] = fmaxf(v[k] * 2.f - 1.f, -1.f);
-    if (!p.hdr) v[k] = fminf(v[k], 1.f);
-    v[k] *= oscale;
-  }
-  return make_float3(v[0], v[1], v[2]);
-}
-
-__device__ __forceinline__ float output_scale(const Transfer& tf)
-{
-  const float s = tf.input_scale_ptr ? *tf.input_scale_ptr : tf.input_scale;
-  return s != 0.f ? 1.f / s : 0.f; // core/color.h:95-123
-}
-
 __global__ void __launch_bounds__(256) output_process_kernel(const OutputParams p)
 {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,7 +288,7 @@ __global__ void __launch_bounds__(256) output_process_kernel(const OutputParams 
   const __half* s = p.src + ((size_t)(h + p.tile.hSrcBegin) * p.TW + (w + p.tile.wSrcBegin)) * p.C;
   const uint2 raw = *reinterpret_cast<const uint2*>(s); // channels 0..3
   const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
-  const float3 v = output_pixel(p, output_scale(p.tf), __low2float(h01), __high2float(h01), __low2float(h23));
+  const float3 v = output_pixel(p.tf, p.hdr, p.snorm, p.dst.C == 1, output_scale(p.tf), __low2float(h01), __high2float(h01), __low2float(h23));
   img_set3(p.dst, h + p.tile.hDstBegin, w + p.tile.wDstBegin, v);
 }
 
@@ -425,7 +321,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) output_process_rows_kernel(con
     const int px = j * 32 + lane;
     if (px >= npx) continue;
     const __half2 h01 = *reinterpret_cast<const __half2*>(&raw[j].x), h23 = *reinterpret_cast<const __half2*>(&raw[j].y);
-    const float3 v = output_pixel(p, oscale, __low2float(h01), __high2float(h01), __low2float(h23));
+    const float3 v = output_pixel(p.tf, p.hdr, p.snorm, p.dst.C == 1, oscale, __low2float(h01), __high2float(h01), __low2float(h23));
     float* q = &stage[warp][px * 3];
     q[0] = v.x; q[1] = v.y; q[2] = v.z;
   }

@@ -45,8 +45,9 @@ class ConvOp:
     i = capi.ConvInfo(); capi.lib().oidnb200_conv_get_info(self.h, C.byref(i))
     return {n: getattr(i, n) for n, _ in capi.ConvInfo._fields_}
 
-  def run(self, src1, src2, w_oihw, bias, I1, I2, simt=False):
-    """src1/src2: torch fp16 [H][W][Cpad] cuda; w_oihw: np.float16 [O][I1+I2][3][3]; bias np.float16 [O]."""
+  def run(self, src1, src2, w_oihw, bias, I1, I2, simt=False, fused=None):
+    """src1/src2: torch fp16 [H][W][Cpad] cuda; w_oihw: np.float16 [O][I1+I2][3][3]; bias np.float16 [O].
+    fused = (capi.Tile, capi.Transfer, hdr, snorm, capi.Image): output process inside the epilogue."""
     import torch
     L = capi.lib()
     O = w_oihw.shape[0]
@@ -62,6 +63,9 @@ class ConvOp:
     check(L.oidnb200_conv_bind(self.h, src1.data_ptr(), src2.data_ptr() if src2 is not None else None,
                                dw.data_ptr(), db.data_ptr(), out.data_ptr()))
     st = torch.cuda.current_stream().cuda_stream
+    if fused is not None:
+      tile, tf, hdr, snorm, img = fused
+      check(L.oidnb200_conv_set_output_process(self.h, C.byref(tile), C.byref(tf), hdr, snorm, C.byref(img)))
     if simt:
       scratch = torch.empty((d.H, d.W, d.Cout), dtype=torch.float16, device="cuda")
       check(L.oidnb200_conv_launch_simt(self.h, scratch.data_ptr(), st))

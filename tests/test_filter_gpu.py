@@ -122,6 +122,32 @@ def test_tiled_equals_untiled_bit_exact_and_inplace(device, oracle):
   f.release()
 
 
+@pytest.mark.parametrize("filt,mode", [("RT", "hdr"), ("RT", "ldr"), ("RTLightmap", "hdr"), ("RTLightmap", "dir")])
+def test_fused_output_process_equals_separate_pass(filt, mode, device):
+  """Device parameter fuseOutput: the output process inside dec_conv0's epilogue (default) against
+  the reference's separate pass, bit for bit, single tile and forced multi-tile."""
+  W, H = 700, 420
+  ic = 9 if (filt, mode) == ("RT", "hdr") else 3
+  tza = weights.model_tza("base", ic, seed=0)
+  imgs = synth.benchmark_images(W, H, hdr=(mode == "hdr"), seed=6)
+  color = imgs["color"] * 2 - 1 if mode == "dir" else imgs["color"]
+  kw = dict(albedo=imgs["albedo"], normal=imgs["normal"]) if ic == 9 else {}
+  params = dict(hdr=(mode == "hdr")) if filt == "RT" else (dict(directional=True) if mode == "dir" else {})
+  res = {}
+  try:
+    for fuse in (1, 0):
+      device.set("fuseOutput", fuse)
+      for tiled in (False, True):
+        extra = dict(maxMemoryMB=0) if tiled else {}
+        res[fuse, tiled], info = run_filter(device, tza, color, filt=filt, **kw, **params, **extra)
+        assert (info["tileCountH"] * info["tileCountW"] > 1) == tiled
+  finally:
+    device.set("fuseOutput", 1)
+  assert np.isfinite(res[1, False]).all() and not np.any(res[1, False] == -123.0)
+  for k in ((1, True), (0, False), (0, True)):
+    np.testing.assert_array_equal(res[1, False].view(np.uint32), res[k].view(np.uint32))
+
+
 def test_large_model_tiles(device, oracle):
   W, H = 1200, 1000
   tza = weights.model_tza("large", 9, seed=0)

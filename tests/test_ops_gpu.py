@@ -187,6 +187,64 @@ def test_output_process(tf, hdr, snorm, fmt, oracle):
   np.testing.assert_allclose(got[finite], r[finite], rtol=(2e-3 if dtype == "float16" else 2e-5), atol=1e-6)
 
 
+@pytest.mark.parametrize("tf,hdr,snorm", TF_CASES)
+@pytest.mark.parametrize("geom", [(70, 300, dict(hSrcBegin=16, wSrcBegin=32, hDstBegin=5, wDstBegin=9, H=50, W=201)),
+                                  (33, 128, dict(hSrcBegin=0, wSrcBegin=0, hDstBegin=0, wDstBegin=0, H=33, W=128)),
+                                  (16, 40, dict(hSrcBegin=15, wSrcBegin=39, hDstBegin=2, wDstBegin=1, H=1, W=1))])
+def test_conv_fused_output_process_equals_separate_pass(tf, hdr, snorm, geom):
+  """The last conv with the output process in its epilogue (oidnb200_conv_set_output_process) writes
+  bit-identical pixels to conv + oidnb200_output_process_launch, touches nothing outside the tile's
+  rectangle and does not write its tensor."""
+  H, W, tile = geom
+  rng = np.random.default_rng(11)
+  I, O = 32, 3
+  src = torch.from_numpy(_rand_half(rng, (H, W, I))).cuda()
+  w = (rng.standard_normal((O, I, 3, 3)) * 0.05).astype(np.float16)
+  b = np.array([0.1, -0.2, 0.3], np.float16)   # one channel mostly negative before the ReLU
+  IH, IW = 64, 256
+  scale_t = torch.tensor([0.25 if hdr else 1.0], dtype=torch.float32, device="cuda")
+  gt = capi.Tile(*[tile[n] for n, _ in capi.Tile._fields_])
+  st = torch.cuda.current_stream().cuda_stream
+  for scale_ptr in (None, scale_t.data_ptr()):
+    gtf = capi.Transfer(tf, 0.25 if hdr else 1.0, scale_ptr)
+    # separate pass
+    op = ConvOp(H, W, 32, 0, 16, relu=1)
+    tensor = op.run(src, None, w, b, I, 0)
+    img_a = torch.full((IH, IW + 3, 3), -7.0, dtype=torch.float32, device="cuda")[:, :IW]   # padded rows
+    check(capi.lib().oidnb200_output_process_launch(tensor.data_ptr(), H, W, 16, C.byref(gt), C.byref(gtf), hdr, snorm,
+                                                    C.byref(image_of(img_a)), st))
+    # fused
+    img_b = torch.full((IH, IW + 3, 3), -7.0, dtype=torch.float32, device="cuda")[:, :IW]
+    op2 = ConvOp(H, W, 32, 0, 16, relu=1)
+    t2 = op2.run(src, None, w, b, I, 0, fused=(gt, gtf, hdr, snorm, image_of(img_b)))
+    torch.cuda.synchronize()
+    a = img_a.cpu().numpy(); bb = img_b.cpu().numpy()
+    np.testing.assert_array_equal(a.view(np.uint32), bb.view(np.uint32))
+    inside = np.zeros((IH, IW), bool)
+    inside[tile["hDstBegin"]:tile["hDstBegin"] + tile["H"], tile["wDstBegin"]:tile["wDstBegin"] + tile["W"]] = True
+    assert np.all(bb[~inside] == -7.0) and np.all(bb[inside] != -7.0)
+    assert bool(torch.isnan(t2).all()), "the fused conv must not store its tensor"
+    # removing the fusion restores the plain conv
+    check(capi.lib().oidnb200_conv_set_output_process(op2.h, None, None, 0, 0, None))
+    check(capi.lib().oidnb200_conv_launch(op2.h, st)); torch.cuda.synchronize()
+    assert torch.equal(t2, tensor)
+
+
+def test_conv_fused_output_process_rejects_what_it_cannot_write():
+  gt = capi.Tile(0, 0, 0, 0, 8, 8)
+  gtf = capi.Transfer(capi.TF_LINEAR, 1.0, None)
+  half_img = torch.zeros((8, 8, 3), dtype=torch.float16, device="cuda")
+  mono_img = torch.zeros((8, 8, 1), dtype=torch.float32, device="cuda")
+  rgb_img = torch.zeros((8, 8, 3), dtype=torch.float32, device="cuda")
+  last = ConvOp(8, 8, 32, 0, 16)
+  for img in (half_img, mono_img):
+    assert capi.lib().oidnb200_conv_set_output_process(last.h, C.byref(gt), C.byref(gtf), 0, 0, C.byref(image_of(img))) == -2
+  wide = ConvOp(8, 8, 32, 0, 32)
+  assert capi.lib().oidnb200_conv_set_output_process(wide.h, C.byref(gt), C.byref(gtf), 0, 0, C.byref(image_of(rgb_img))) == -2
+  big = capi.Tile(0, 0, 0, 0, 9, 8)
+  assert capi.lib().oidnb200_conv_set_output_process(last.h, C.byref(big), C.byref(gtf), 0, 0, C.byref(image_of(rgb_img))) == -1
+
+
 @pytest.mark.parametrize("W,H", [(37, 21), (64, 48), (130, 70), (1920, 1080), (5, 3)])
 @pytest.mark.parametrize("dtype", ["float32", "float16"])
 def test_autoexposure(W, H, dtype, oracle):
