@@ -25,6 +25,7 @@ Device::Device(const std::vector<int>& ids, const std::vector<void*>& streams)
   // with little memory. Tiling is then driven by the number of engines / shards only.
   maxTilePixels = 7680L * 4352L;
   if (const char* e = getenv("OIDN_B200_TILE_POLICY")) tilePolicy = atoi(e);
+  if (const char* e = getenv("OIDN_B200_FUSE_OUTPUT")) fuseOutput = atoi(e);
   if (const char* e = getenv("OIDN_B200_MAX_TILE_PIXELS")) maxTilePixels = atol(e);
   if (const char* e = getenv("OIDN_B200_GRAPH")) graph = atoi(e);
   if (const char* e = getenv("OIDN_B200_WEIGHTS_DIR")) weightsDir = e;

@@ -18,9 +18,11 @@ constexpr int kMaxChunks   = 8;     // K chunks (<=64 channels each) over both s
 constexpr int kMaxOutChunks = 3;    // output-channel pieces (64/32/16) of one CoutG group
 constexpr int kMaxStages   = 24;    // A-operand pipeline depth (per stream)
 constexpr int kConvThreads = 384;   // 2 x (TMA warp + MMA warp) + 2 x 4 epilogue warps
+constexpr int kConvThreads4 = 768;  // four-stream variant (CoutG <= 32): 4 x (TMA + MMA warp) + 4 x 4 epilogue warps
+constexpr int kMaxStreams  = 4;
 constexpr int kStripW      = 128;   // output pixels per MMA tile (UMMA M)
 constexpr int kMaxStageBytes = 17408; // one A stage: up to 132 px x 128 B, 1024-aligned (64-channel chunk)
-constexpr int kSmemHeader  = 2048;  // barriers + TMEM pointer (1.5 KB) + bias (512 B)
+constexpr int kSmemHeader  = 4096;  // barriers + TMEM pointer (3 KB) + bias (512 B)
 constexpr int kTmemCols    = 512;
 constexpr int kMaxSlots    = 16;
 constexpr int kSmemBudget  = 232448; // 227 KB opt-in dynamic shared memory per CTA
@@ -83,12 +85,17 @@ struct ConvKernelParams
   uint32_t chunk_bblk16[kMaxChunks]; // chunk_bblk / 16
   int      H, W;                    // conv resolution (= resolution of the unpooled output)
   int      CoutG, ngroups, CoutPad; // output channels per CTA group / groups / padded total
-  int      nstreams;                // 1 or 2 independent row streams per CTA
+  int      nstreams;                // 1, 2 or 4 independent row streams per CTA
   int      R;                       // TMEM accumulator ring slots per stream (nstreams*R*CoutG <= 512)
   int      RC, nstrips, nrowchunks; // rows per work item, strips across W, row chunks down H
   int      nstages;                 // A pipeline stages per stream
   int      prefetch_rows;           // > 0: the TMA producer prefetches input rows this far ahead into L2
-  uint32_t stage_bytes;             // bytes of one A stage: 132 px x the widest K chunk, 1024-aligned
+  uint32_t stage_bytes;             // bytes of the widest A stage: 132 px x the widest K chunk, 1024-aligned
+  uint32_t ring_bytes;              // bytes of one stream's A ring
+  uint32_t stage_off[kMaxStages];   // byte offset of stage s inside the stream's ring. When nstages is a
+                                    // multiple of nchunks, stage s always holds chunk s % nchunks and is
+                                    // sized for it (narrow chunks take less room: deeper ring); otherwise
+                                    // every stage has stage_bytes
   uint32_t w_bytes;                 // total weight bytes TMA-loaded per CTA
   uint32_t b_bytes;                 // size of the resident weight region (1024-aligned blocks)
   int      nout;                    // output pieces of the group
@@ -96,7 +103,12 @@ struct ConvKernelParams
   int      out_cc[kMaxOutChunks];   // channels in the piece (64/32/16)
   uint32_t out_off[kMaxOutChunks];  // byte offset of the piece inside one staging slice
   uint32_t out_buf_bytes;           // bytes of one staging slice (one warp, one row)
-  int      out_nbuf;                // 1 or 2 staging slices per epilogue warp (8 warps)
+  int      out_nbuf;                // 1 or 2 staging slices per epilogue warp (8 warps; 16 with four streams)
+  int      direct_store;            // 1: the epilogue stores its pixels straight from registers to global
+                                    // memory (32-byte stores), no staging slices and no TMA store: the
+                                    // shared memory goes to A stages instead
+  void*    out_ptr;                 // destination tensor [Hd][Wd][CoutPad] fp16 (direct_store)
+  int      out_W;                   // Wd
   int      relu, post_op;
   const float* bias;                // fp32 [CoutAlloc]
   unsigned long long* trace;        // [12 warps][16 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null

@@ -189,7 +189,7 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
     }
     return align_up(off, 1024);
   };
-  constexpr uint32_t kEpiWarps = 8;
+  constexpr uint32_t kEpiWarps = 8;   // sizing of CoutG assumes the two-stream kernel with staged stores
   int CoutG = std::min(d.Cout, 128);
   while (CoutG > 16 && b_bytes(CoutG) + kEpiWarps * out_bytes(CoutG) + min_stages * stage_bytes > avail) CoutG -= 16;
   if (b_bytes(CoutG) + kEpiWarps * out_bytes(CoutG) + min_stages * stage_bytes > avail)
@@ -239,27 +239,70 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   }
   kp.out_buf_bytes = align_up(ooff, 1024);
 
-  // What is left after the weights and the staging slices goes to A stages. Two streams need a
-  // 4-slot accumulator ring each (CoutG <= 64) and >= 2 stages each. Staging is double-buffered
-  // (a warp's store of row i overlaps its work on row i+1) unless that would cost a stream or
-  // leave fewer than 3 stages per stream.
-  auto config = [&](int nbuf, int& nstreams, int& nstages) {
-    const uint32_t left = avail - bbytes - kEpiWarps * nbuf * kp.out_buf_bytes;
-    const int total_stages = (int)(left / stage_bytes);
-    nstreams = (CoutG <= 64 && total_stages >= 4) ? 2 : 1;
-    nstages = std::min(total_stages / nstreams, kMaxStages);
-  };
-  int ns1, st1, ns2 = 0, st2 = 0;
-  config(1, ns1, st1);
-  const bool fits2 = bbytes + kEpiWarps * 2 * kp.out_buf_bytes + min_stages * stage_bytes <= avail;
-  if (fits2) config(2, ns2, st2);
-  if (fits2 && ns2 == ns1 && st2 >= std::min(3, st1))
+  // What is left after the weights and the epilogue's staging slices goes to A stages.
+  // A stage of chunk c: 132 pixels x its channels, 1024-aligned. A ring whose stage count is a multiple
+  // of the chunk count gives every stage a fixed chunk, so narrow chunks take narrow stages.
+  uint32_t chunk_stage[kMaxChunks], row_bytes = 0;
+  for (int c = 0; c < n; ++c)
   {
-    kp.out_nbuf = 2; kp.nstreams = ns2; kp.nstages = st2;
+    chunk_stage[c] = align_up(132u * kp.chunk_cc[c] * 2u, 1024);
+    row_bytes += chunk_stage[c];
   }
-  else
+  auto ring = [&](uint32_t left, int& nstages, bool& by_row) { // one stream's ring inside `left` bytes
+    const int uni = std::min((int)(left / stage_bytes), kMaxStages);
+    const int rows = std::min((int)(left / row_bytes), kMaxStages / n);
+    by_row = rows * n > uni;
+    nstages = by_row ? rows * n : uni;
+  };
+  // Candidates, best first. Streams: a stream serialises "wait for the row, issue its MMAs, commit"
+  // on one issuing thread, so two independent streams per CTA keep the tensor pipe busy (CoutG <= 64:
+  // two >= 4-slot accumulator rings fit TMEM); every stream needs >= 2 A stages. Measured on the 4K
+  // shapes (profiles/r01_probe4_direct_streams.log, r01_probe5_four_streams.log): a second stream is
+  // worth 8-10 % on dec_conv2a/3a even with a 2-3 stage ring each; FOUR streams (CoutG <= 32, the
+  // 768-thread kernel) gain 6 % on enc_conv0 but lose 3-8 % on enc_conv1 / dec_conv1b / dec_conv0
+  // (4-slot rings, 80 registers per thread), so they are opt-in: OIDN_B200_STREAMS=4.
+  // Epilogue stores: staged through swizzled shared memory + TMA store, double-buffered if that
+  // leaves >= 3 stages per stream, else single-buffered, else straight from registers (frees all
+  // staging memory; measured 0-5 % slower at equal stream count, so it is only used to afford
+  // another stream). OIDN_B200_STREAMS (max streams) and OIDN_B200_DIRECT_STORE (0/1) override.
+  int max_streams = CoutG <= 64 ? 2 : 1;
+  if (const char* e = getenv("OIDN_B200_STREAMS"))
+    max_streams = std::min(CoutG <= 32 ? 4 : max_streams, std::max(1, atoi(e)));
+  int force_direct = -1;
+  if (const char* e = getenv("OIDN_B200_DIRECT_STORE")) force_direct = atoi(e);
+  bool by_row = false, found = false;
+  for (int ns = max_streams; ns >= 1 && !found; ns >>= 1)
   {
-    kp.out_nbuf = 1; kp.nstreams = ns1; kp.nstages = st1;
+    if (ns == 3) continue;
+    const uint32_t epi_warps = ns == 4 ? 16u : 8u;
+    for (int nbuf = 2; nbuf >= 0 && !found; --nbuf)   // nbuf 0 = direct stores
+    {
+      if (force_direct == 1 && nbuf != 0) continue;
+      if (force_direct == 0 && nbuf == 0) continue;
+      const uint32_t fixed = bbytes + epi_warps * nbuf * kp.out_buf_bytes;
+      if (fixed + (uint32_t)ns * 2u * stage_bytes > avail) continue;
+      int nst; bool br;
+      ring(((avail - fixed) / ns) & ~1023u, nst, br);
+      const int want = nbuf == 2 ? 3 : 2;
+      if (nst < want) continue;
+      kp.nstreams = ns; kp.nstages = nst; kp.out_nbuf = nbuf; by_row = br; found = true;
+    }
+  }
+  if (!found)
+  {
+    set_error("conv: no shared-memory configuration fits");
+    return OIDNB200_ERR_UNSUPPORTED;
+  }
+  kp.direct_store = kp.out_nbuf == 0 ? 1 : 0;
+  const uint32_t epi_warps = kp.nstreams == 4 ? 16u : 8u;
+  {
+    uint32_t off = 0;
+    for (int s2 = 0; s2 < kp.nstages; ++s2)
+    {
+      kp.stage_off[s2] = off;
+      off += by_row ? chunk_stage[s2 % n] : stage_bytes;
+    }
+    kp.ring_bytes = off;
   }
   kp.R = std::min(kMaxSlots, (kTmemCols / kp.nstreams) / CoutG);
   // A ring that cannot hold even one input row (all K chunks) does not hide HBM latency: the TMA
@@ -268,8 +311,8 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   // OIDN_B200_PREFETCH overrides the choice (hardware probing only).
   kp.prefetch_rows = (kp.nstages < n) ? 2 : 0;
   if (const char* e = getenv("OIDN_B200_PREFETCH")) kp.prefetch_rows = atoi(e);
-  pl.smem = 1024 + kSmemHeader + (size_t)kp.nstreams * kp.nstages * stage_bytes + bbytes +
-            (size_t)kEpiWarps * kp.out_nbuf * kp.out_buf_bytes;
+  pl.smem = 1024 + kSmemHeader + (size_t)kp.nstreams * kp.ring_bytes + bbytes +
+            (size_t)epi_warps * kp.out_nbuf * kp.out_buf_bytes;
 
   // Work decomposition: strips of 128 px x RC rows; pick RC minimising the critical path.
   kp.H = d.H; kp.W = d.W;
@@ -352,6 +395,8 @@ static int plan_bind(ConvPlan& pl, const void* src1, const void* src2, const voi
     }
   }
   pl.dst = dst;
+  kp.out_ptr = dst;
+  kp.out_W = d.post_op == POST_POOL ? d.W / 2 : d.W;
   kp.bias = static_cast<const float*>(bias);
   pl.src1 = src1; pl.src2 = src2; pl.weights = weights;
   pl.bound = true;

@@ -45,7 +45,7 @@ using namespace ptx;
 #define TRACE_DECL long long tr[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_start = clock64(); long long tr_t = 0;
 #define MBAR_WAIT(bar, par, tag) do { const long long t0_ = clock64(); mbar_wait(bar, par, tag); tr[tag] += clock64() - t0_; } while (0)
 #define TRACE_WRAP(tag, stmt) do { const long long t0_ = clock64(); stmt; tr[tag] += clock64() - t0_; } while (0)
-#define TRACE_FLUSH() do { if (p.trace && lane == 0) { tr[0] = clock64() - tr_start; \
+#define TRACE_FLUSH() do { if (p.trace && lane == 0 && warp < 12) { tr[0] = clock64() - tr_start; \
   for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&p.trace[warp * 16 + i_], (unsigned long long)tr[i_]); } } while (0)
 #define TRACE_ARGS , tr, tr_t
 #define TRACE_PARAMS , long long* tr, long long& tr_t
@@ -67,13 +67,13 @@ namespace {
 struct SmemLayout
 {
   // byte offsets from the 1024-aligned base; [stream][index] arrays
-  static constexpr uint32_t full_a     = 0;                                  // 2 x kMaxStages x 8
-  static constexpr uint32_t empty_a    = full_a + 2 * 8 * kMaxStages;
-  static constexpr uint32_t w_full     = empty_a + 2 * 8 * kMaxStages;
-  static constexpr uint32_t tmem_full  = w_full + 8;                         // 2 x kMaxSlots x 8
-  static constexpr uint32_t tmem_empty = tmem_full + 2 * 8 * kMaxSlots;
-  static constexpr uint32_t tmem_ptr   = tmem_empty + 2 * 8 * kMaxSlots;
-  static constexpr uint32_t bias       = 1536;                               // 128 floats
+  static constexpr uint32_t full_a     = 0;                                  // kMaxStreams x kMaxStages x 8
+  static constexpr uint32_t empty_a    = full_a + kMaxStreams * 8 * kMaxStages;
+  static constexpr uint32_t w_full     = empty_a + kMaxStreams * 8 * kMaxStages;
+  static constexpr uint32_t tmem_full  = w_full + 8;                         // kMaxStreams x kMaxSlots x 8
+  static constexpr uint32_t tmem_empty = tmem_full + kMaxStreams * 8 * kMaxSlots;
+  static constexpr uint32_t tmem_ptr   = tmem_empty + kMaxStreams * 8 * kMaxSlots;
+  static constexpr uint32_t bias       = 3072;                               // 128 floats
   static constexpr uint32_t a_ring     = kSmemHeader;
 };
 static_assert(SmemLayout::tmem_ptr + 4 <= SmemLayout::bias && SmemLayout::bias + 512 <= kSmemHeader, "barrier block overflows");
@@ -115,6 +115,13 @@ __device__ __forceinline__ uint32_t max_half2(uint32_t a, uint32_t b)
   return r;
 }
 
+__device__ __forceinline__ void st_global_32B(void* ptr, const uint32_t* h)
+{
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(ptr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7])
+               : "memory");
+}
+
 // All tcgen05.mma of one staged (row, K-chunk): 3 horizontal taps x NK k-steps x (1 or 2) runs,
 // fully unrolled so that each MMA costs two descriptor adds plus the issue.
 template <int NK, bool TWO>
@@ -146,6 +153,7 @@ struct EpiCtx
   uint32_t sbase, tmem_base, b_region;
   uint8_t* sgen;
   int warp, lane, group, cta, nctas;
+  int epi_warp0;   // first epilogue warp of the CTA (4, or 8 in the four-stream kernel)
 };
 
 // Bias add (fp32, packed pairs) + fp16 rounding (+ReLU) of W accumulator columns; W = 16 or 32.
@@ -169,7 +177,9 @@ __device__ __forceinline__ void bias_cvt(const uint32_t (&v)[W], const float2* b
 //   pair) -> smem slice -> TMA store.
 // max commutes with the monotonic "+bias, round" so pooling after rounding is bit-identical to
 // pooling the rounded full-resolution tensor (what the reference's separate pool pass does).
-template <int NB, bool POOL>
+// WIDE: 32-column TMEM loads where a piece allows (fewer, larger loads); the four-stream kernel
+// (80 registers per thread) uses 16-column loads only.
+template <int NB, bool POOL, bool WIDE>
 __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx& ec TRACE_PARAMS)
 {
   constexpr int CoutG = NB * 16;
@@ -178,15 +188,18 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
   const int warp = ec.warp, lane = ec.lane;
   const int NST  = p.nstreams;
   const int R    = p.R;
-  const int wg   = (warp - 4) >> 2;           // 0 or 1
-  const int st   = (NST == 2) ? wg : 0;       // stream drained by this warpgroup
+  const int wg   = (warp - ec.epi_warp0) >> 2; // epilogue warpgroup: 0..1 (0..3 with four streams)
+  const int st   = (NST >= 2) ? wg : 0;       // stream drained by this warpgroup
   const bool alternate = (NST == 1);
   const int vcta = ec.cta * NST + st, nv = ec.nctas * NST;
   const int nitems = p.nstrips * p.nrowchunks;
   const int q    = warp & 3;                  // TMEM lane quarter this warp may access
   const bool relu = p.relu != 0;
+  const bool direct = p.direct_store != 0;   // registers -> global memory, no staging / TMA store
   const int nbuf = p.out_nbuf;
   const uint32_t wregion = ec.b_region + p.b_bytes + (uint32_t)((wg * 4 + q) * nbuf) * p.out_buf_bytes;
+  const int gch0 = ec.group * CoutG;           // first output channel of this CTA's group
+  __half* const gout = static_cast<__half*>(p.out_ptr) + gch0;
   const uint32_t tfull  = ec.sbase + SmemLayout::tmem_full + 8 * st * kMaxSlots;
   const uint32_t tempty = ec.sbase + SmemLayout::tmem_empty + 8 * st * kMaxSlots;
   const int spix = POOL ? (lane >> 1) : lane; // staging row of this thread's pixel inside the warp slice
@@ -220,6 +233,7 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
   {
     const Item it = get_item(p, item);
     const int xo = (POOL ? (it.x0 >> 1) : it.x0) + q * PROWS;
+    const bool gwriter = writer && (xo + spix) < p.out_W;   // direct stores clip at the tensor edge themselves
     uint32_t y_mod = a_mod, y_par = a_par;
     for (int y = it.y0; y <= it.y1; y += (POOL ? 2 : 1), ++rown)
     {
@@ -239,12 +253,16 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
         MBAR_WAIT(tfull + 8 * slot1, par1, 6);
       tc_fence_after();
       // this warp's staging slice `buf` must have been read out by the TMA store that used it last
-      if (lane == 0)
+      if (!direct)
       {
-        TRACE_WRAP(7, if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>());
+        if (lane == 0)
+        {
+          TRACE_WRAP(7, if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>());
+        }
+        __syncwarp();
       }
-      __syncwarp();
       TRACE_BEGIN();
+      __half* const gpix = gout + ((size_t)(POOL ? (y >> 1) : y) * p.out_W + (xo + spix)) * p.CoutPad;
       const uint32_t t0 = lane_base + slot0 * CoutG;
       const uint32_t t1 = lane_base + slot1 * CoutG;
       const uint32_t stage_out = wregion + buf * p.out_buf_bytes;
@@ -256,9 +274,9 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
         const uint32_t rowaddr = stage_out + prow[oc];
         const uint32_t xr = pxor[oc];
 #pragma unroll
-        for (int j = 0; j < ccw; j += 32)
+        for (int j = 0; j < ccw; j += (WIDE ? 32 : 16))
         {
-          if (ccw - j >= 32)
+          if (WIDE && ccw - j >= 32)
           {
             uint32_t v[32], h[16];
             tmem_ld32(t0 + c0 + j, v);
@@ -279,7 +297,16 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
 #pragma unroll
               for (int i = 0; i < 16; ++i) h[i] = max_half2(h[i], __shfl_xor_sync(0xffffffffu, h[i], 1));
             }
-            if (writer)
+            if (direct)
+            {
+              // the last group may reach past the tensor's channels (CoutAlloc > CoutPad): clip per 16
+              if (gwriter)
+              {
+                if (gch0 + c0 + j < p.CoutPad)      st_global_32B(gpix + c0 + j, &h[0]);
+                if (gch0 + c0 + j + 16 < p.CoutPad) st_global_32B(gpix + c0 + j + 16, &h[8]);
+              }
+            }
+            else if (writer)
             {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -308,7 +335,11 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
 #pragma unroll
               for (int i = 0; i < 8; ++i) h[i] = max_half2(h[i], __shfl_xor_sync(0xffffffffu, h[i], 1));
             }
-            if (writer)
+            if (direct)
+            {
+              if (gwriter && gch0 + c0 + j < p.CoutPad) st_global_32B(gpix + c0 + j, &h[0]);
+            }
+            else if (writer)
             {
 #pragma unroll
               for (int k = 0; k < 2; ++k)
@@ -321,7 +352,7 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
       // Release the accumulator slot(s) back to the MMA issuer (one arrive per warp), make the
       // generic-proxy smem writes visible to the TMA engine, then store this warp's pixels.
       tc_fence_before();
-      fence_proxy_async();
+      if (!direct) fence_proxy_async();
       __syncwarp();
       TRACE_END(10);
       if (lane == 0)
@@ -329,11 +360,14 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
         mbar_arrive(tempty + 8 * slot0);
         if (POOL)
           mbar_arrive(tempty + 8 * slot1);
-        const int yo = POOL ? (y >> 1) : y;
+        if (!direct)
+        {
+          const int yo = POOL ? (y >> 1) : y;
 #pragma unroll
-        for (int oc = 0; oc < NP; ++oc)
-          tma_store_3d(&p.omap[oc], stage_out + out_piece_off(NB, oc, PROWS), ec.group * CoutG + out_piece_c0(NB, oc), xo, yo);
-        bulk_commit();
+          for (int oc = 0; oc < NP; ++oc)
+            tma_store_3d(&p.omap[oc], stage_out + out_piece_off(NB, oc, PROWS), ec.group * CoutG + out_piece_c0(NB, oc), xo, yo);
+          bulk_commit();
+        }
       }
       TRACE_END(11);
       if (++buf == (uint32_t)nbuf) buf = 0;
@@ -359,8 +393,8 @@ __device__ __forceinline__ void epilogue_fused_output(const ConvKernelParams& p,
   const int warp = ec.warp, lane = ec.lane;
   const int NST  = p.nstreams;
   const int R    = p.R;
-  const int wg   = (warp - 4) >> 2;
-  const int st   = (NST == 2) ? wg : 0;
+  const int wg   = (warp - ec.epi_warp0) >> 2;
+  const int st   = (NST >= 2) ? wg : 0;
   const bool alternate = (NST == 1);
   const int vcta = ec.cta * NST + st, nv = ec.nctas * NST;
   const int nitems = p.nstrips * p.nrowchunks;
@@ -428,9 +462,15 @@ __device__ __forceinline__ void epilogue_fused_output(const ConvKernelParams& p,
 
 } // namespace
 
-__global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
+// NSTMAX = 2: 384 threads (warps 0-3 producers, 4-11 epilogue); NSTMAX = 4: 768 threads (warps 0-7
+// producers, 8-23 epilogue), launched only with p.nstreams == 4 (CoutG <= 32: four accumulator rings
+// of >= 4 slots fit the 512 TMEM columns). More streams = more threads issuing tcgen05.mma: the narrow
+// layers are bound by how fast ONE thread can issue (a 128x96x16 MMA is 48 tensor-pipe cycles).
+template <int NSTMAX>
+__device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
 {
+  constexpr int kProducerWarps = 2 * NSTMAX;
+  constexpr int kThreads = (kProducerWarps + 4 * NSTMAX) * 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -448,8 +488,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   const int nitems  = p.nstrips * p.nrowchunks;
   const int NS      = p.nstages;                // A stages per stream
   const int R       = p.R;                      // accumulator ring slots per stream
-  const uint32_t stage_bytes = p.stage_bytes;
-  const uint32_t b_region = sbase + SmemLayout::a_ring + (uint32_t)(NST * NS) * stage_bytes;
+  const uint32_t ring_bytes = p.ring_bytes;   // one stream's A ring
+  const uint32_t b_region = sbase + SmemLayout::a_ring + (uint32_t)NST * ring_bytes;
 
   // ---------------------------------------------------------------- setup
   if (warp == 0 && lane == 0)
@@ -480,10 +520,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
     tmem_alloc(sbase + SmemLayout::tmem_ptr, kTmemCols);
     tmem_relinquish();
   }
-  if (warp >= 4)
+  if (warp >= kProducerWarps)
   {
     float* bias_s = reinterpret_cast<float*>(sgen + SmemLayout::bias);
-    for (int i = threadIdx.x - 128; i < p.CoutG; i += kConvThreads - 128)
+    for (int i = threadIdx.x - kProducerWarps * 32; i < p.CoutG; i += kThreads - kProducerWarps * 32)
       bias_s[i] = p.bias[group * p.CoutG + i];
   }
   tc_fence_before();
@@ -494,7 +534,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
 
   // Both single-issuer roles keep warp-uniform control flow (all 32 lanes walk the loops, one
   // elected lane issues): values stay in uniform registers instead of being broadcast per use.
-  if (warp < 4)
+  if (warp < kProducerWarps)
   {
     const int st = warp >> 1;                     // stream of this TMA / MMA warp
     if (st < NST)
@@ -502,7 +542,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
       const int vcta = cta * NST + st, nv = nctas * NST; // streams are independent "virtual CTAs"
       const uint32_t full_a  = sbase + SmemLayout::full_a + 8 * st * kMaxStages;
       const uint32_t empty_a = sbase + SmemLayout::empty_a + 8 * st * kMaxStages;
-      const uint32_t a_ring  = sbase + SmemLayout::a_ring + (uint32_t)(st * NS) * stage_bytes;
+      const uint32_t a_ring  = sbase + SmemLayout::a_ring + (uint32_t)st * ring_bytes;
       const bool leader = elect_one();
       // -------------------------------------------------------------- TMA producer
       if ((warp & 1) == 0)
@@ -550,7 +590,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
             for (int c = 0; c < p.nchunks; ++c)
             {
               const uint32_t full = full_a + 8 * s;
-              const uint32_t dst  = a_ring + s * stage_bytes;
+              const uint32_t dst  = a_ring + p.stage_off[s];
               MBAR_WAIT(empty_a + 8 * s, ph ^ 1, 1);
               const int cc = p.chunk_cc[c];
               if (leader)
@@ -589,9 +629,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
         const uint32_t max_run = min(3u, 256u / CoutG);
         const uint32_t idesc1 = umma_idesc_f16(CoutG);
         const uint32_t sbase16 = (sbase & 0x3FFFFu) >> 4;
-        const uint32_t ring16  = sbase16 + ((SmemLayout::a_ring + (uint32_t)(st * NS) * stage_bytes) >> 4);
-        const uint32_t stage16 = stage_bytes >> 4;
-        const uint32_t breg16  = sbase16 + ((SmemLayout::a_ring + (uint32_t)(NST * NS) * stage_bytes) >> 4);
+        const uint32_t ring16  = sbase16 + ((SmemLayout::a_ring + (uint32_t)st * ring_bytes) >> 4);
+        const uint32_t breg16  = sbase16 + ((SmemLayout::a_ring + (uint32_t)NST * ring_bytes) >> 4);
         const int nchunks = p.nchunks;
         MBAR_WAIT(sbase + SmemLayout::w_full, 0, 2);
         tc_fence_after();
@@ -633,7 +672,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
               const uint32_t nk     = p.chunk_nk[c];                 // 16-channel k-steps: 1, 2 or 4
               const uint32_t row16  = nk * 2;                        // row bytes / 16
               const uint32_t hi     = p.chunk_hi[c];                 // SBO, version, swizzle
-              const uint32_t a_lo   = ring16 + stage * stage16 + p.chunk_a16[c]; // upsampled rows start at x0-2
+              const uint32_t a_lo   = ring16 + (p.stage_off[stage] >> 4) + p.chunk_a16[c]; // upsampled rows start at x0-2
               const uint32_t b_lo   = breg16 + p.chunk_b16[c];
               const uint32_t bblk16 = p.chunk_bblk16[c];
               const uint32_t rb0 = brow0 * row16, rb1 = brow1 * row16;
@@ -696,15 +735,27 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
     EpiCtx ec;
     ec.sbase = sbase; ec.tmem_base = tmem_base; ec.b_region = b_region; ec.sgen = sgen;
     ec.warp = warp; ec.lane = lane; ec.group = group; ec.cta = cta; ec.nctas = nctas;
+    ec.epi_warp0 = kProducerWarps;
     if (p.fo.enabled)
       epilogue_fused_output(p, ec TRACE_ARGS);
     else
     switch ((p.CoutG >> 4) * 2 + (p.post_op == POST_POOL ? 1 : 0))
     {
-#define EPI_CASE(NB) case (NB) * 2: epilogue<NB, false>(p, ec TRACE_ARGS); break; case (NB) * 2 + 1: epilogue<NB, true>(p, ec TRACE_ARGS); break;
-      EPI_CASE(1) EPI_CASE(2) EPI_CASE(3) EPI_CASE(4) EPI_CASE(5) EPI_CASE(6) EPI_CASE(7) EPI_CASE(8)
+#define EPI_CASE(NB) case (NB) * 2: epilogue<NB, false, NSTMAX == 2>(p, ec TRACE_ARGS); break; case (NB) * 2 + 1: epilogue<NB, true, NSTMAX == 2>(p, ec TRACE_ARGS); break;
+      EPI_CASE(1) EPI_CASE(2)
 #undef EPI_CASE
-      default: break;
+      default:
+        if constexpr (NSTMAX == 2)
+        {
+          switch ((p.CoutG >> 4) * 2 + (p.post_op == POST_POOL ? 1 : 0))
+          {
+#define EPI_CASE(NB) case (NB) * 2: epilogue<NB, false, true>(p, ec TRACE_ARGS); break; case (NB) * 2 + 1: epilogue<NB, true, true>(p, ec TRACE_ARGS); break;
+            EPI_CASE(3) EPI_CASE(4) EPI_CASE(5) EPI_CASE(6) EPI_CASE(7) EPI_CASE(8)
+#undef EPI_CASE
+            default: break;
+          }
+        }
+        break;
     }
   }
 
@@ -719,6 +770,18 @@ conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
   }
 }
 
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ ConvKernelParams p)
+{
+  conv3x3_tc_body<2>(p);
+}
+
+__global__ void __launch_bounds__(kConvThreads4, 1)
+conv3x3_tc_kernel_s4(const __grid_constant__ ConvKernelParams p)
+{
+  conv3x3_tc_body<4>(p);
+}
+
 cudaError_t conv3x3_tc_launch(const ConvKernelParams& p, int grid, size_t smem_bytes, cudaStream_t stream)
 {
   // the opt-in shared-memory attribute is per device
@@ -730,16 +793,19 @@ cudaError_t conv3x3_tc_launch(const ConvKernelParams& p, int grid, size_t smem_b
   {
     e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(conv3x3_tc_kernel_s4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
+  const bool four = p.nstreams == 4;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kConvThreads);
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(four ? kConvThreads4 : kConvThreads);
   cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, p);
+  return four ? cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel_s4, p) : cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, p);
 }
 
 } // namespace oidnb200

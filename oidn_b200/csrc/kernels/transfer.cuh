@@ -70,18 +70,29 @@ __device__ __forceinline__ float tf_forward(const Transfer& t, float y)
   }
 }
 
+// Inverse transfer function of the output process. The segment formulas are evaluated branch-free
+// (a warp's pixels fall in different segments) with multiplications by the reciprocal constants and
+// the power through the SFU (lg2.approx / ex2.approx, relative error of the result < 4e-6 on the
+// segment's range); expf stays libdevice's (2 ulp). This function runs per pixel in the epilogue of
+// the last convolution, where libdevice's powf and IEEE divisions made the epilogue warps the
+// bottleneck. (The reference's CPU device evaluates these with ISPC's approximate math library.)
 __device__ __forceinline__ float tf_inverse(const Transfer& t, float x)
 {
   switch (t.type)
   {
   case OIDNB200_TF_SRGB:
-    return x <= kSrgbX0 ? x / kSrgbA : powf((x - kSrgbD) / kSrgbB, 1.f / kSrgbC);
+  {
+    const float lin = x * (1.f / kSrgbA);
+    const float pw  = __powf((x - kSrgbD) * (1.f / kSrgbB), 1.f / kSrgbC);
+    return x <= kSrgbX0 ? lin : pw;
+  }
   case OIDNB200_TF_PU:
   {
-    const float u = x * t.rcp_norm;
-    if (u <= kPuX0) return u / kPuA;
-    if (u <= kPuX1) return powf((u - kPuD) / kPuB, 1.f / kPuC);
-    return expf((u - kPuG) / kPuE) - kPuF;
+    const float u   = x * t.rcp_norm;
+    const float lin = u * (1.f / kPuA);
+    const float pw  = __powf((u - kPuD) * (1.f / kPuB), 1.f / kPuC);
+    const float ex  = expf((u - kPuG) * (1.f / kPuE)) - kPuF;
+    return u <= kPuX0 ? lin : (u <= kPuX1 ? pw : ex);
   }
   case OIDNB200_TF_LOG:
     return expf(x * t.rcp_norm) - 1.f;

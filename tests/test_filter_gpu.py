@@ -126,7 +126,7 @@ def test_tiled_equals_untiled_bit_exact_and_inplace(device, oracle):
 def test_fused_output_process_equals_separate_pass(filt, mode, device):
   """Device parameter fuseOutput: the output process inside dec_conv0's epilogue (default) against
   the reference's separate pass, bit for bit, single tile and forced multi-tile."""
-  W, H = 700, 420
+  W, H = 1500, 900
   ic = 9 if (filt, mode) == ("RT", "hdr") else 3
   tza = weights.model_tza("base", ic, seed=0)
   imgs = synth.benchmark_images(W, H, hdr=(mode == "hdr"), seed=6)
