@@ -139,7 +139,7 @@ class ShardedFilter:
   upload_tiles()); each rank uploads only the source rectangles of its own tiles."""
 
   def __init__(self, dist, torch, device, W, H, tza, hdr=True, quality=api.QUALITY_HIGH, clean_aux=False,
-               aux=True, frame=None, stage=True, source="rank0"):
+               aux=True, frame=None, stage=True, source="rank0", own_groups=True):
     assert source in ("rank0", "distributed")
     self.dist, self.torch, self.dev = dist, torch, device
     self.rank, self.world = dist.get_rank(), dist.get_world_size()
@@ -170,6 +170,12 @@ class ShardedFilter:
       self.local["output"] = self.bufs["output"] if self.rank == 0 else device.new_buffer(nb)
     self.scale = torch.ones(1, dtype=torch.float32, device="cuda")
     self.token = torch.zeros(1, dtype=torch.float32, device="cuda")
+    # Own communicators per filter: collectives on ONE communicator execute in issue order whatever
+    # stream they are on, so with the default group frame f+1's exchange (start of its stream) would
+    # wait for frame f's join (end of the other stream) and two frames in flight would not overlap.
+    # new_group is collective: every rank creates its filters in the same order.
+    self.pg_exchange = dist.new_group() if own_groups else None   # start-of-frame exchange (bins / scale)
+    self.pg_join = dist.new_group() if own_groups else None       # end-of-frame join
     f = device.new_filter("RT")
     for n in names:
       f.set_image(n, self.local[n], capi.FORMAT_FLOAT3, W, H)
@@ -246,28 +252,28 @@ class ShardedFilter:
           if L.oidnb200_autoexposure_bins_launch(C.byref(self.ae_img), bh0, bh1, bw0, bw1, self.bins_local.data_ptr(), st) != 0:
             raise RuntimeError(L.oidnb200_last_error().decode())
         self.bins_all.copy_(self.bins_local)
-        dist.all_reduce(self.bins_all)          # the exchange step: every rank gets the complete bin array
+        dist.all_reduce(self.bins_all, group=self.pg_exchange)   # the exchange step: every rank gets the complete bin array
         if L.oidnb200_autoexposure_reduce_launch(self.bins_all.data_ptr(), self.nbins, self.scale.data_ptr(), st) != 0:
           raise RuntimeError(L.oidnb200_last_error().decode())
       self.filter.execute_async()
       if assemble and self.rank != 0:
         self._copy_rects(("output",), False)    # NVLink DMA: local interior rectangles -> rank 0's output
-      dist.all_reduce(self.token)               # join: every rank's rectangles are where they belong
+      dist.all_reduce(self.token, group=self.pg_join)   # join: every rank's rectangles are where they belong
       return
     if self.hdr:
       if self.rank == 0:
         rc = L.oidnb200_autoexposure_launch(C.byref(self.ae_img), self.ae_scratch.data_ptr(), self.scale.data_ptr(), st)
         if rc != 0:
           raise RuntimeError(L.oidnb200_last_error().decode())
-      dist.broadcast(self.scale, src=0)       # also orders the peers after rank 0's frame upload
+      dist.broadcast(self.scale, src=0, group=self.pg_exchange)   # also orders the peers after rank 0's frame upload
     else:
-      dist.all_reduce(self.token)             # frame-start ordering without a scale
+      dist.all_reduce(self.token, group=self.pg_exchange)   # frame-start ordering without a scale
     if self.staged:
       self._copy_rects(self.inputs, True)     # NVLink DMA: rank 0 -> local tile inputs (with overlap)
     self.filter.execute_async()
     if self.staged:
       self._copy_rects(("output",), False)    # NVLink DMA: local interior rectangles -> rank 0's output
-    dist.all_reduce(self.token)               # join: every rank's rectangles are in rank 0's output
+    dist.all_reduce(self.token, group=self.pg_join)   # join: every rank's rectangles are in rank 0's output
 
   def release(self):
     self.filter.release()
@@ -282,6 +288,10 @@ class ShardedFilter:
     if self.rank == 0:
       for b in self.bufs.values():
         b.release()
+    for g in (self.pg_exchange, self.pg_join):
+      if g is not None:
+        self.dist.destroy_process_group(g)
+    self.pg_exchange = self.pg_join = None
 
 
 def bench_main(args, rank, world, local_rank):
