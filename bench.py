@@ -124,8 +124,7 @@ def cpu_port_throughput(tza, W, H, budget_s=20.0):
   Only place besides tests/ and smoke() that executes oracle/ (as the reported CPU baseline)."""
   sys.path.insert(0, os.path.join(ROOT, "oracle"))
   import oracle as orc
-  orc.lib()
-  cores = os.cpu_count() or 1
+  cores = orc.lib().oro_set_num_threads(os.cpu_count() or 1)   # the threads actually used
   best = None
   for w, h in ((480, 272), (960, 544), (1920, 1080), (W, H)):
     if w > W or h > H:
@@ -150,8 +149,8 @@ def run_reference(args, rank):
   W, H = args.width, args.height
   sys.path.insert(0, os.path.join(ROOT, "oracle"))
   import oracle as orc
-  orc.lib()
-  cores = os.cpu_count() or 1
+  # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for all host cores, report what is in effect
+  cores = orc.lib().oro_set_num_threads(os.cpu_count() or 1)
   # one step = one bounded sample (a crop of the workload sized for ~2-4 s on this host)
   probe = cpu_port_throughput(tza, 480, 272, budget_s=1.0)
   px = max(480 * 272, min(W * H, int(probe["value"] * 1e6 * 3.0)))

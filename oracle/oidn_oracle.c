@@ -19,6 +19,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ORO_API __attribute__((visibility("default")))
 
@@ -61,6 +64,20 @@ static uint16_t f2h(float f)
   uint32_t out = (x - 0x38000000u) >> 13, rem = x & 0x1FFFu;
   if (rem > 0x1000u || (rem == 0x1000u && (out & 1))) out++;
   return (uint16_t)(sign | out);
+}
+
+/* Host threads of the parallel loops. Launchers such as torchrun export OMP_NUM_THREADS=1 to their
+ * workers; the timed CPU baseline (bench.py) asks for the cores it reports instead. Returns the
+ * thread count in effect. */
+ORO_API int oro_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
 }
 
 ORO_API float oro_half_to_float(uint16_t h) { return h2f(h); }
@@ -230,7 +247,7 @@ typedef struct
 static void img_get3(const oro_image* im, int h, int w, float v[3])
 {
   const uint8_t* px = (const uint8_t*)im->ptr + (size_t)h * im->row_stride + (size_t)w * im->pixel_stride;
-  float c[3];
+  float c[3] = {0.f, 0.f, 0.f};
   for (int i = 0; i < im->C; ++i) c[i] = im->is_half ? h2f(((const uint16_t*)px)[i]) : ((const float*)px)[i];
   /* image_accessor.h:36-41: C==2 -> (x,y,y), C==1 -> (x,x,x) */
   v[0] = c[0]; v[1] = im->C >= 2 ? c[1] : c[0]; v[2] = im->C == 3 ? c[2] : (im->C == 2 ? c[1] : c[0]);

@@ -51,6 +51,7 @@ def lib():
   if _lib is None:
     build()
     L = C.CDLL(_LIB)
+    L.oro_set_num_threads.restype = C.c_int; L.oro_set_num_threads.argtypes = [C.c_int]
     L.oro_tf_forward.restype = C.c_float; L.oro_tf_forward.argtypes = [C.c_int, C.c_float]
     L.oro_tf_inverse.restype = C.c_float; L.oro_tf_inverse.argtypes = [C.c_int, C.c_float]
     L.oro_tf_norm_scale.restype = C.c_float; L.oro_tf_norm_scale.argtypes = [C.c_int]

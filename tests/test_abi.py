@@ -65,3 +65,81 @@ def test_conv_planner_runs_without_gpu():
     assert i.ngroups * i.cout_group >= Co and i.nstreams * i.ring_slots * i.cout_group <= 512
     assert i.nstrips == -(-W // 128) and i.nrowchunks * i.rows_per_item >= H
     L.oidnb200_conv_destroy(h)
+
+
+def test_conv_planner_stream_and_store_choices(monkeypatch):
+  """Every UNet layer shape (base, small, large) plans inside the hardware limits under the default rules and
+  under the probing overrides; the concat layers of the base net get their second stream from the
+  direct-store epilogue (out_nbuf == 0), narrow layers keep staged stores."""
+  L = capi.lib()
+  from oidn_b200 import weights
+  shapes = set()
+  for kind, ic in (("base", 9), ("base", 3), ("small", 3), ("large", 9)):
+    prev_out = 0
+    for name, cin, cout in weights.unet_layers(kind, ic):
+      n = int(name[8])                                  # enc_convN.. / dec_convN..
+      level = max(n - 1, 0)
+      concat = name.startswith("dec") and name.endswith("a")
+      in1 = prev_out if concat else cin
+      in2 = cin - in1 if concat else 0
+      pool = name.startswith("enc") and 1 <= n <= 4 and (kind != "large" or name.endswith("b"))
+      pad = lambda c: -(-c // 16) * 16
+      shapes.add((name if (kind, ic) == ("base", 9) else "", 2160 >> level, 3840 >> level, pad(in1), pad(in2) if in2 else 0,
+                  pad(cout), int(pool), int(concat)))
+      prev_out = cout
+  assert len(shapes) > 30
+
+  def plan(shape):
+    _, H, W, c1, c2, co, post, up = shape
+    d = capi.ConvDesc(H, W, c1, c2, co, 1, post, up, 0); h = C.c_void_p()
+    assert L.oidnb200_conv_create(C.byref(d), C.byref(h)) == 0, (shape, L.oidnb200_last_error())
+    i = capi.ConvInfo(); L.oidnb200_conv_get_info(h, C.byref(i)); L.oidnb200_conv_destroy(h)
+    assert 1 <= i.grid <= 148 and i.smem_bytes <= 232448, shape
+    assert i.nstreams in (1, 2, 4) and 2 <= i.nstages <= 24 and 0 <= i.out_nbuf <= 2, shape
+    assert i.nstreams * i.ring_slots * i.cout_group <= 512 and i.ring_slots >= 4, shape
+    assert i.nstreams == 1 or i.cout_group <= (32 if i.nstreams == 4 else 64), shape
+    return i
+
+  base = {s[0]: plan(s) for s in shapes if s[0]}
+  for s in shapes:
+    plan(s)
+  assert all(i.nstreams <= 2 for i in base.values())                       # four streams are opt-in
+  assert base["dec_conv2a"].nstreams == 2 and base["dec_conv2a"].out_nbuf == 0
+  assert base["dec_conv3a"].nstreams == 2 and base["dec_conv3a"].out_nbuf == 0
+  assert base["enc_conv0"].out_nbuf == 2 and base["dec_conv1a"].out_nbuf >= 1 and base["dec_conv1a"].nstreams == 2
+  for env in ({"OIDN_B200_STREAMS": "4"}, {"OIDN_B200_STREAMS": "1"}, {"OIDN_B200_DIRECT_STORE": "1"},
+              {"OIDN_B200_DIRECT_STORE": "0", "OIDN_B200_STREAMS": "2"}):
+    for k, v in env.items():
+      monkeypatch.setenv(k, v)
+    infos = [plan(s) for s in shapes]
+    if env.get("OIDN_B200_STREAMS") == "4":
+      assert any(i.nstreams == 4 for i in infos)
+    if env.get("OIDN_B200_STREAMS") == "1":
+      assert all(i.nstreams == 1 for i in infos)
+    if env.get("OIDN_B200_DIRECT_STORE") == "1":
+      assert all(i.out_nbuf == 0 for i in infos)
+    for k in env:
+      monkeypatch.delenv(k)
+
+
+def test_fused_output_process_argument_checks_without_gpu():
+  """oidnb200_conv_set_output_process validates on the host: only the 16-channel last conv and packed fp32 RGB
+  images are accepted, the tile must lie inside tensor and image, NULL removes the fusion."""
+  L = capi.lib()
+  mk = lambda co: (lambda d, h: (L.oidnb200_conv_create(C.byref(d), C.byref(h)), h)[1])(capi.ConvDesc(64, 256, 32, 0, co, 1, 0, 0, 0), C.c_void_p())
+  last, wide = mk(16), mk(32)
+  tf = capi.Transfer(capi.TF_PU, 1.0, None)
+  img = lambda fmt, ps, rs, W=256, H=64: capi.Image(0x1000, fmt, W, H, ps, rs)
+  ok_tile, bad_tile = capi.Tile(0, 0, 0, 0, 64, 256), capi.Tile(0, 0, 0, 0, 65, 256)
+  f3 = capi.FORMAT_FLOAT + 2
+  assert L.oidnb200_conv_set_output_process(last, C.byref(ok_tile), C.byref(tf), 1, 0, C.byref(img(f3, 12, 256 * 12))) == 0
+  assert L.oidnb200_conv_set_output_process(last, None, None, 0, 0, None) == 0
+  assert L.oidnb200_conv_set_output_process(wide, C.byref(ok_tile), C.byref(tf), 1, 0, C.byref(img(f3, 12, 256 * 12))) == -2
+  assert L.oidnb200_conv_set_output_process(last, C.byref(ok_tile), C.byref(tf), 1, 0, C.byref(img(capi.FORMAT_HALF + 2, 6, 256 * 6))) == -2
+  assert L.oidnb200_conv_set_output_process(last, C.byref(ok_tile), C.byref(tf), 1, 0, C.byref(img(f3, 16, 256 * 16))) == -2
+  assert L.oidnb200_conv_set_output_process(last, C.byref(bad_tile), C.byref(tf), 1, 0, C.byref(img(f3, 12, 256 * 12))) == -1
+  bad_tf = capi.Transfer(99, 1.0, None)
+  assert L.oidnb200_conv_set_output_process(last, C.byref(ok_tile), C.byref(bad_tf), 1, 0, C.byref(img(f3, 12, 256 * 12))) == -1
+  assert L.oidnb200_last_error()
+  for h in (last, wide):
+    L.oidnb200_conv_destroy(h)
