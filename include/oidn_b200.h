@@ -140,6 +140,11 @@ OIDNB200_API void oidnb200PlanTiles(int H, int W, int largeModel, int deviceMinA
  * grid whose tile count is divisible by numUnits (engines x shards) and recomputes the fewest pixels. */
 OIDNB200_API void oidnb200PlanTilesMinOverlap(int H, int W, int largeModel, int deviceMinAlignment, int numUnits,
                                               long maxTilePixels, oidnb200_tile_plan* plan);
+/* "tilePolicy" = 2 (opt-in): as above, with tile widths costed in whole 128-pixel conv strips per UNet
+ * level (a 2064-wide tile is 17 strips, not 16.1): 8K over 8 units becomes 2x4 tiles of 3936x1232
+ * instead of 4x2 of 2064x2256. */
+OIDNB200_API void oidnb200PlanTilesStripAware(int H, int W, int largeModel, int deviceMinAlignment, int numUnits,
+                                              long maxTilePixels, oidnb200_tile_plan* plan);
 /* Tile rectangles of a plan, 12 ints each (hSrc,wSrc,hBuf,wBuf,H1,W1,hOutBuf,wOutBuf,hDst,wDst,H2,W2);
  * returns the tile count; writes at most maxTiles tiles. */
 OIDNB200_API int oidnb200EnumerateTiles(const oidnb200_tile_plan* plan, int* out, int maxTiles);

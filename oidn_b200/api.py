@@ -268,9 +268,11 @@ class Filter:
 
 def plan_tiles(H, W, large=False, dev_alignment=1, num_engines=1, max_tile_pixels=2160 * 2160, policy=0):
   """Tile planner alone (no GPU): returns (plan dict, [tile rect dicts]). policy 0 = the reference's
-  search (core/unet_filter.cpp:254-335), 1 = this backend's default (fewest recomputed pixels)."""
+  search (core/unet_filter.cpp:254-335), 1 = this backend's default (fewest recomputed pixels),
+  2 = fewest 128-pixel conv strips (opt-in)."""
   p = capi.TilePlan()
-  fn = capi.lib().oidnb200PlanTilesMinOverlap if policy else capi.lib().oidnb200PlanTiles
+  L = capi.lib()
+  fn = (L.oidnb200PlanTiles, L.oidnb200PlanTilesMinOverlap, L.oidnb200PlanTilesStripAware)[int(policy)]
   fn(H, W, int(large), dev_alignment, num_engines, max_tile_pixels, C.byref(p))
   n = p.tileCountH * p.tileCountW
   out = (C.c_int * (12 * n))()

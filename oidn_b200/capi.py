@@ -133,6 +133,7 @@ FILTER_ABI = {
   "oidnb200ResetFilterProfile": (None, [C.c_void_p]),
   "oidnb200PlanTiles": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(TilePlan)]),
   "oidnb200PlanTilesMinOverlap": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(TilePlan)]),
+  "oidnb200PlanTilesStripAware": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.POINTER(TilePlan)]),
   "oidnb200EnumerateTiles": (C.c_int, [C.POINTER(TilePlan), C.POINTER(C.c_int), C.c_int]),
   "oidnb200ParseTZA": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p)]),
   "oidnb200PlanArena": (C.c_size_t, [C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -439,6 +439,15 @@ void oidnb200PlanTilesMinOverlap(int H, int W, int largeModel, int deviceMinAlig
                             p.tileAlignment, p.tileOverlap};
 }
 
+void oidnb200PlanTilesStripAware(int H, int W, int largeModel, int deviceMinAlignment, int numUnits, long maxTilePixels,
+                                  oidnb200_tile_plan* out)
+{
+  const TilePlan p = planTilesMinOverlap(H, W, largeModel != 0, deviceMinAlignment, numUnits > 0 ? numUnits : 1,
+                                         maxTilePixels > 0 ? maxTilePixels : 7680L * 4352L, [](const TilePlan&) { return true; }, true);
+  *out = oidnb200_tile_plan{p.H, p.W, p.tileH, p.tileW, p.tilePadH, p.tilePadW, p.tileCountH, p.tileCountW,
+                            p.tileAlignment, p.tileOverlap};
+}
+
 int oidnb200EnumerateTiles(const oidnb200_tile_plan* pl, int* out, int maxTiles)
 {
   TilePlan p;

@@ -81,8 +81,24 @@ TilePlan planTiles(int H, int W, bool largeModel, int deviceMinAlignment, int nu
 // divisible by numUnits is costed and the one that recomputes the fewest pixels wins. On a B200
 // memory rarely forces tiling, the number of GPUs/engines does: 8K on 2 GPUs becomes 1x2 tiles
 // (+4 % pixels) where the halving search gives 3x2 (+10 %).
+// stripAware (tilePolicy=2, opt-in until measured at 8 GPUs): the conv kernel works in strips of 128
+// pixels at every UNet level, so a 2064-wide tile costs 17 strips at full resolution (and 9, 5, 3, 2
+// at the pooled levels), not 16.1: the width enters the cost rounded up to whole strips per level,
+// weighted by the level's share of the FLOPs.
+static double effectiveWidth(int tileW)
+{
+  static const double share[5] = {0.583, 0.248, 0.124, 0.040, 0.005}; // base UNet, SURVEY.md section 8(d) table by level
+  double w = 0;
+  for (int l = 0; l < 5; ++l)
+  {
+    const int wl = tileW >> l;
+    w += share[l] * (double)(ceil_div(wl, 128) * 128) * (double)(1 << l);
+  }
+  return w;
+}
+
 TilePlan planTilesMinOverlap(int H, int W, bool largeModel, int deviceMinAlignment, int numUnits, long maxTilePixels,
-                             const std::function<bool(const TilePlan&)>& fits)
+                             const std::function<bool(const TilePlan&)>& fits, bool stripAware)
 {
   constexpr int minAlign = 16;
   TilePlan base;
@@ -123,7 +139,8 @@ TilePlan planTilesMinOverlap(int H, int W, bool largeModel, int deviceMinAlignme
       p.tileCountH = ch; p.tileCountW = cw;
       if ((long)p.tileH * p.tileW > maxTilePixels) continue;
       // cost: pixels pushed through the network per unit (tiles are dealt round-robin), then fewer tiles
-      const double cost = (double)(ch * cw / numUnits) * p.tileH * p.tileW + 1e-3 * ch * cw;
+      const double cost = (double)(ch * cw / numUnits) * p.tileH * (stripAware ? effectiveWidth(p.tileW) : (double)p.tileW) +
+                          1e-3 * ch * cw;
       if (found && cost >= bestCost) continue;
       if (!fits(p)) continue;
       best = p; bestCost = cost; found = true;
@@ -556,9 +573,10 @@ void UNetFilter::init()
 
   const auto fits = [&](const TilePlan& c) { return buildModel(c, maxMemoryByteSize, false); };
   const int units = device->getNumEngines() * numShards;
-  plan = device->getInt("tilePolicy") == 0
+  const int policy = device->getInt("tilePolicy");
+  plan = policy == 0
            ? planTiles(H, W, largeModel, device->getMinTileAlignment(), units, maxTilePixels, fits)
-           : planTilesMinOverlap(H, W, largeModel, device->getMinTileAlignment(), units, maxTilePixels, fits);
+           : planTilesMinOverlap(H, W, largeModel, device->getMinTileAlignment(), units, maxTilePixels, fits, policy == 2);
   if (!buildModel(plan, SIZE_MAX, true)) throw std::runtime_error("could not build filter model");
   tiles = enumerateTiles(plan);
 

@@ -81,8 +81,9 @@ struct TileRect
 TilePlan planTiles(int H, int W, bool largeModel, int deviceMinAlignment, int numEngines, long maxTilePixels,
                    const std::function<bool(const TilePlan&)>& fits);
 // Own search (device parameter tilePolicy=1, the default): the grid with the fewest recomputed pixels.
+// stripAware (tilePolicy=2): tile widths count in whole 128-pixel conv strips per UNet level.
 TilePlan planTilesMinOverlap(int H, int W, bool largeModel, int deviceMinAlignment, int numUnits, long maxTilePixels,
-                             const std::function<bool(const TilePlan&)>& fits);
+                             const std::function<bool(const TilePlan&)>& fits, bool stripAware = false);
 std::vector<TileRect> enumerateTiles(const TilePlan& plan);
 
 class UNetFilter : public Filter

@@ -90,6 +90,25 @@ def test_min_overlap_tilings_8k():
     assert (p["tileCountW"], p["tileCountH"], p["tileW"], p["tileH"]) == (cw, ch, tw, th), (n, p)
 
 
+@pytest.mark.parametrize("H,W", SIZES)
+@pytest.mark.parametrize("units", [1, 2, 4, 8])
+def test_strip_aware_planner(H, W, units):
+  """tilePolicy=2 (opt-in): same geometry invariants; tile widths are costed in whole 128-pixel conv strips,
+  so it never needs more strip-rows per unit than the default search."""
+  def strips(p):   # full-resolution strip-rows per unit
+    return (p["tileCountH"] * p["tileCountW"] // units) * p["tileH"] * -(-p["tileW"] // 128)
+  for max_px in (7680 * 4352, 1000 * 1000):
+    base, _ = api.plan_tiles(H, W, False, 1, units, max_px, policy=1)
+    got, tiles = api.plan_tiles(H, W, False, 1, units, max_px, policy=2)
+    check_tiles(H, W, got, tiles)
+    assert (got["tileCountH"] * got["tileCountW"]) % units == 0 or (base["tileCountH"] * base["tileCountW"]) % units != 0
+    assert got["tileH"] * got["tileW"] <= max_px or base["tileH"] * base["tileW"] > max_px
+  p, _ = api.plan_tiles(4320, 7680, False, 1, 8, 7680 * 4352, policy=2)
+  assert (p["tileCountW"], p["tileCountH"], p["tileW"], p["tileH"]) == (2, 4, 3936, 1232), p
+  q, _ = api.plan_tiles(4320, 7680, False, 1, 8, 7680 * 4352, policy=1)
+  assert strips(p) < strips(q)
+
+
 def parse(blob):
   msg = C.c_char_p()
   buf = (C.c_char * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
