@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -107,7 +108,7 @@ static int num_sms()
 
 static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
+static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_streams = 0 /* 0 = the planner's rule */)
 {
   if (d.H <= 0 || d.W <= 0 || d.C1 <= 0 || d.C1 % 16 || d.C2 < 0 || d.C2 % 16 || d.Cout <= 0 || d.Cout % 16)
   {
@@ -266,6 +267,7 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl)
   // staging memory; measured 0-5 % slower at equal stream count, so it is only used to afford
   // another stream). OIDN_B200_STREAMS (max streams) and OIDN_B200_DIRECT_STORE (0/1) override.
   int max_streams = CoutG <= 64 ? 2 : 1;
+  if (want_streams == 4 && CoutG <= 32) max_streams = 4;
   if (const char* e = getenv("OIDN_B200_STREAMS"))
     max_streams = std::min(CoutG <= 32 ? 4 : max_streams, std::max(1, atoi(e)));
   int force_direct = -1;
@@ -480,6 +482,12 @@ using namespace oidnb200;
 struct oidnb200_conv
 {
   ConvPlan plan;
+  // The network's last conv (16 padded output channels) with the output process in its epilogue is
+  // bound by the per-pixel math of the epilogue warps, not by MMA issue or HBM: the four-stream
+  // kernel has 16 epilogue warps instead of 8 (measured in the 4K frame: dec_conv0 + output 0.166 ->
+  // 0.143 ms, while the UNfused conv is 7 % slower with four streams). So a conv that can be fused
+  // keeps a second, four-stream plan that oidnb200_conv_launch uses while a fusion is set.
+  std::unique_ptr<ConvPlan> fused_plan;
 };
 
 extern "C" {
@@ -497,6 +505,12 @@ int oidnb200_conv_create(const oidnb200_conv_desc* desc, oidnb200_conv** out)
   {
     delete c;
     return rc;
+  }
+  if (desc->Cout == 16 && desc->post_op == POST_NONE && c->plan.kp.ngroups == 1)
+  {
+    c->fused_plan.reset(new ConvPlan());
+    if (plan_create(*desc, *c->fused_plan, 4) != 0 || c->fused_plan->kp.nstreams != 4)
+      c->fused_plan.reset();   // does not fit: the fused conv runs on the default plan
   }
   *out = c;
   return 0;
@@ -554,7 +568,9 @@ int oidnb200_conv_pack_bias(const oidnb200_conv* conv, const uint16_t* b_x, int 
 int oidnb200_conv_bind(oidnb200_conv* conv, const void* src1, const void* src2, const void* weights,
                        const void* bias, void* dst)
 {
-  return plan_bind(conv->plan, src1, src2, weights, bias, dst);
+  const int rc = plan_bind(conv->plan, src1, src2, weights, bias, dst);
+  if (rc == 0 && conv->fused_plan) return plan_bind(*conv->fused_plan, src1, src2, weights, bias, dst);
+  return rc;
 }
 
 int oidnb200_conv_set_output_process(oidnb200_conv* conv, const oidnb200_tile* tile, const oidnb200_transfer* tf,
@@ -565,6 +581,7 @@ int oidnb200_conv_set_output_process(oidnb200_conv* conv, const oidnb200_tile* t
   if (!dst)
   {
     fo.enabled = 0;
+    if (conv->fused_plan) conv->fused_plan->kp.fo.enabled = 0;
     return 0;
   }
   const oidnb200_conv_desc& d = pl.desc;
@@ -600,12 +617,13 @@ int oidnb200_conv_set_output_process(oidnb200_conv* conv, const oidnb200_tile* t
   fo.tf_type = t.type; fo.norm = t.norm; fo.rcp_norm = t.rcp_norm;
   fo.input_scale = t.input_scale; fo.input_scale_ptr = t.input_scale_ptr;
   fo.hdr = hdr; fo.snorm = snorm;
+  if (conv->fused_plan) conv->fused_plan->kp.fo = fo;
   return 0;
 }
 
 int oidnb200_conv_launch(const oidnb200_conv* conv, oidnb200_stream stream)
 {
-  const ConvPlan& pl = conv->plan;
+  const ConvPlan& pl = (conv->plan.kp.fo.enabled && conv->fused_plan) ? *conv->fused_plan : conv->plan;
   if (!pl.bound)
   {
     set_error("conv_launch: op not bound");
