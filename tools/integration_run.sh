@@ -1,0 +1,14 @@
+#!/bin/bash
+# The reference's own oidnBenchmark and oidnTest (unmodified sources) running on oidn_b200 through the reference's
+# public API: baseline/_b200 is built by tools/build_integration_module.sh.
+export LD_LIBRARY_PATH=$PWD/baseline/_b200/lib
+export OIDN_B200_WEIGHTS_DIR=$PWD/baseline/_b200/weights
+mkdir -p gpurun_out
+{
+baseline/_b200/bin/oidnBenchmark --ld
+timeout 30 baseline/_b200/bin/oidnBenchmark -d cuda -r "RT\.hdr_alb_nrm\.(1920x1080|3840x2160)" -q high
+timeout 20 baseline/_b200/bin/oidnBenchmark -d cuda -r "RTLightmap\.hdr\.4096x4096"
+timeout ${1:-40} baseline/_b200/bin/oidnTest --device cuda
+echo "oidnTest exit=$?"
+} > gpurun_out/integration_run.log 2>&1
+tail -40 gpurun_out/integration_run.log
