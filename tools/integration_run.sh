@@ -4,6 +4,7 @@
 export LD_LIBRARY_PATH=$PWD/baseline/_b200/lib
 export OIDN_B200_WEIGHTS_DIR=$PWD/baseline/_b200/weights
 mkdir -p gpurun_out
+cp -f oidn_b200/liboidn_b200.so baseline/_b200/lib/   # the library as built now, not as it was when the module was linked
 {
 baseline/_b200/bin/oidnBenchmark --ld
 timeout 30 baseline/_b200/bin/oidnBenchmark -d cuda -r "RT\.hdr_alb_nrm\.(1920x1080|3840x2160)" -q high
