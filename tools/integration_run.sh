@@ -1,6 +1,7 @@
 #!/bin/bash
 # The reference's own oidnBenchmark and oidnTest (unmodified sources) running on oidn_b200 through the reference's
-# public API: baseline/_b200 is built by tools/build_integration_module.sh.
+# public API: baseline/_b200 is built by tools/build_integration_module.sh. It is listed in .gpurunignore (109 MB):
+# comment that line out before sending this script to the GPU box.
 export LD_LIBRARY_PATH=$PWD/baseline/_b200/lib
 export OIDN_B200_WEIGHTS_DIR=$PWD/baseline/_b200/weights
 mkdir -p gpurun_out
