@@ -29,7 +29,7 @@ mma_issue_kernel(int N, int issuers, int tiles, int count, Result* out)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   // layout: [0,64) barriers (one per warp), [64,68) tmem pointer, from 1024: per warp A tile (128 rows x 128 B) and
   // B tile (256 rows x 128 B)
   const uint32_t bar = sbase + 8 * warp;
