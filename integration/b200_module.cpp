@@ -10,6 +10,13 @@
 // (oidnNewBuffer, oidnRead/WriteBuffer) stay the reference's own USMBuffer on top of this engine's usmAlloc/usmCopy
 // (core/engine.h:78-91). The op factories of the Engine (newConv, ...) are never reached on this route: they throw.
 //
+// Built with -DOIDN_B200_OP_LEVEL the same file gives INTEGRATION.md's op-level route instead: NO core change at
+// all; the reference's own filters, core/graph.cpp, arena planner and tile loop stay in charge and this module
+// only supplies the Engine's ops (Conv incl. fused Pool and the paired ConcatConv, Pool, Upsample, InputProcess,
+// OutputProcess, Autoexposure, ImageCopy) on the kernel-level C ABI (include/oidn_b200_kernels.h). First version:
+// upsampled tensors are materialised (core splits PostOp::Upsample into an Upsample op) and the output process is a
+// pass of its own; the two kernels that ConcatConvHWC asks for are recognised and run as ONE concat-conv.
+//
 // Only interfaces are taken from the reference headers; no reference code is copied.
 #include "core/context.h"
 #include "core/device.h"
@@ -23,8 +30,11 @@
 #include "core/output_process.h"
 #include "core/image_copy.h"
 #include "oidn_b200.h"
+#include "oidn_b200_kernels.h"
 #include <cuda_runtime.h>
 #include <map>
+#include <unordered_map>
+#include <vector>
 
 OIDN_NAMESPACE_BEGIN
 
@@ -44,6 +54,7 @@ OIDN_NAMESPACE_BEGIN
       throw Exception(Error::Unknown, str);
     }
 
+  #if !defined(OIDN_B200_OP_LEVEL)
     // oidn_b200 keeps the reference's error codes (include/oidn_b200.h) and its first-error-per-device slot
     void checkB200(OIDNB200Device h)
     {
@@ -52,6 +63,7 @@ OIDN_NAMESPACE_BEGIN
       if (code != 0)
         throw Exception(static_cast<Error>(code), message ? message : "oidn_b200 error");
     }
+  #endif
   }
 
   class B200PhysicalDevice final : public PhysicalDevice
@@ -83,7 +95,24 @@ OIDN_NAMESPACE_BEGIN
     B200Engine(Device* device, cudaStream_t stream) : device(device), stream(stream) {}
 
     Device* getDevice() const override { return device; }
+    cudaStream_t getStream() const { return stream; }
 
+  #if defined(OIDN_B200_OP_LEVEL)
+    // Pool is fused into the conv's epilogue; PostOp::Upsample is split off by core/graph.cpp:67-80 (first version)
+    bool isConvSupported(PostOp postOp) override { return postOp == PostOp::Pool; }
+    Ref<Conv> newConv(const ConvDesc& desc) override;
+    Ref<Pool> newPool(const PoolDesc& desc) override;
+    Ref<Upsample> newUpsample(const UpsampleDesc& desc) override;
+    Ref<Autoexposure> newAutoexposure(const ImageDesc& srcDesc) override;
+    Ref<InputProcess> newInputProcess(const InputProcessDesc& desc) override;
+    Ref<OutputProcess> newOutputProcess(const OutputProcessDesc& desc) override;
+    Ref<ImageCopy> newImageCopy() override;
+
+    // ConcatConvHWC = conv1{src1, W1, bias, no activation} then conv2{src2, W2, bias = dst tensor, activation}
+    // (core/concat_conv_hwc.cpp:27-31,62-67): conv1 registers under its dst tensor, conv2 finds it by its bias
+    // tensor and the pair runs as one kernel with two K segments.
+    std::unordered_map<const Tensor*, class B200Conv*> convByDst;
+  #else
     Ref<Conv> newConv(const ConvDesc&) override { unsupported(); return nullptr; }
     Ref<Pool> newPool(const PoolDesc&) override { unsupported(); return nullptr; }
     Ref<Upsample> newUpsample(const UpsampleDesc&) override { unsupported(); return nullptr; }
@@ -91,6 +120,7 @@ OIDN_NAMESPACE_BEGIN
     Ref<InputProcess> newInputProcess(const InputProcessDesc&) override { unsupported(); return nullptr; }
     Ref<OutputProcess> newOutputProcess(const OutputProcessDesc&) override { unsupported(); return nullptr; }
     Ref<ImageCopy> newImageCopy() override { unsupported(); return nullptr; }
+  #endif
 
     void* usmAlloc(size_t byteSize, Storage storage) override
     {
@@ -136,10 +166,12 @@ OIDN_NAMESPACE_BEGIN
     void wait() override { checkCuda(cudaStreamSynchronize(stream)); }
 
   private:
+  #if !defined(OIDN_B200_OP_LEVEL)
     static void unsupported()
     {
       throw Exception(Error::InvalidOperation, "the oidn_b200 device builds its own graph: core ops are not created through the engine");
     }
+  #endif
 
     Device* device;
     cudaStream_t stream;
@@ -234,8 +266,14 @@ OIDN_NAMESPACE_BEGIN
         subdevice->getEngine()->wait();
     }
 
+  #if defined(OIDN_B200_OP_LEVEL)
+    // final weights / biases stay in host memory (core/graph.cpp:113-140): the conv repacks them into its own
+    // layout and uploads that
+    bool needWeightAndBiasOnDevice() const override { return false; }
+  #else
     // Needs `virtual` on Device::newFilter (the one-word core change)
     Ref<Filter> newFilter(const std::string& type) override;
+  #endif
 
     OIDNB200Device getHandle() const { return handle; }
 
@@ -274,6 +312,7 @@ OIDN_NAMESPACE_BEGIN
       }
       subdevices.emplace_back(new Subdevice(std::unique_ptr<Engine>(new B200Engine(this, stream))));
 
+    #if !defined(OIDN_B200_OP_LEVEL)
       // the backend runs on the same stream as the core's buffer copies: everything stays stream-ordered
       void* streams[1] = {stream};
       handle = oidnb200NewCUDADevice(&deviceID, streams, 1);
@@ -282,6 +321,7 @@ OIDN_NAMESPACE_BEGIN
       oidnb200SetDeviceInt(handle, "verbose", verbose);
       oidnb200CommitDevice(handle);
       checkB200(handle);
+    #endif
     }
 
     int deviceID = 0;
@@ -291,6 +331,7 @@ OIDN_NAMESPACE_BEGIN
     OIDNB200Device handle = nullptr;
   };
 
+#if !defined(OIDN_B200_OP_LEVEL)
   // core/filter.h on top of the filter-level C ABI. Parameter names, defaults, dirty tracking and error behaviour are
   // those of the reference filters because oidn_b200/csrc/host/filter.cpp mirrors core/unet_filter.cpp, rt_filter.cpp
   // and rtlightmap_filter.cpp; this class only forwards.
@@ -415,6 +456,295 @@ OIDN_NAMESPACE_BEGIN
       std::cout << "Filter: " << type << " (oidn_b200)" << std::endl;
     return makeRef<B200Filter>(Ref<B200Device>(this), type);
   }
+#else
+  // ---------------------------------------------------------------------------------------------------------------
+  // Op-level route: the Engine's ops on the kernel-level C ABI
+  // ---------------------------------------------------------------------------------------------------------------
+  namespace
+  {
+    void checkKernel(int rc, const char* what)
+    {
+      if (rc == 0)
+        return;
+      const std::string msg = std::string(what) + ": " + oidnb200_last_error();
+      if (rc == OIDNB200_ERR_INVALID)     throw Exception(Error::InvalidArgument, msg);
+      if (rc == OIDNB200_ERR_UNSUPPORTED) throw Exception(Error::UnsupportedHardware, msg);
+      if (rc == (int)cudaErrorMemoryAllocation) throw Exception(Error::OutOfMemory, msg);
+      throw Exception(Error::Unknown, msg);
+    }
+
+    oidnb200_image toABI(const Ref<Image>& image)
+    {
+      if (!image || !*image)
+        return oidnb200_image{nullptr, 0, 0, 0, 0, 0};
+      const ImageDesc& d = image->getDesc();
+      return oidnb200_image{image->getPtr(), static_cast<int>(d.format), d.getW(), d.getH(), d.wByteStride, d.hByteStride};
+    }
+
+    oidnb200_transfer toABI(const TransferFunction& tf)
+    {
+      return oidnb200_transfer{static_cast<int>(tf.type), tf.inputScale, tf.inputScalePtr};
+    }
+
+    oidnb200_tile toABI(const Tile& t)
+    {
+      return oidnb200_tile{t.hSrcBegin, t.wSrcBegin, t.hDstBegin, t.wDstBegin, t.H, t.W};
+    }
+  }
+
+  class B200Conv final : public Conv
+  {
+  public:
+    B200Conv(B200Engine* engine, const ConvDesc& desc)
+      : Conv(desc),
+        engine(engine)
+    {
+      if (srcDesc.layout != TensorLayout::hwc || srcDesc.dataType != DataType::Float16 ||
+          weightDesc.layout != TensorLayout::ohwi || weightDesc.dataType != DataType::Float16 ||
+          weightDesc.getH() != 3 || weightDesc.getW() != 3 || postOp == PostOp::Upsample)
+        throw std::invalid_argument("unsupported convolution");
+      accumulate = biasDesc.getRank() == 3; // second half of a ConcatConvHWC: bias = dst, dst += conv
+    }
+
+    ~B200Conv()
+    {
+      if (dst)
+        engine->convByDst.erase(dst.get());
+      release();
+    }
+
+    Engine* getEngine() const override { return engine; }
+
+    void finalize() override
+    {
+      if (!src || !weight || !bias || !dst)
+        throw std::logic_error("convolution source/weight/bias/destination not set");
+      absorbed = false;
+      partner = nullptr;
+      if (accumulate)
+      {
+        auto it = engine->convByDst.find(bias.get());
+        if (it == engine->convByDst.end() || it->second->activation != Activation::None || it->second->accumulate)
+          throw std::logic_error("accumulating convolution without the first half of its ConcatConv");
+        partner = it->second;
+        partner->absorbed = true;   // conv1 becomes a no-op: this op runs both K segments
+      }
+      else if (activation == Activation::None)
+        engine->convByDst[dst.get()] = this; // may be the first half of a ConcatConv
+      prepared = false;
+    }
+
+    void submitKernels(const Ref<CancellationToken>&) override
+    {
+      if (absorbed)
+        return;
+      prepare();
+      bind();
+      checkKernel(oidnb200_conv_launch(handle, engine->getStream()), "conv");
+    }
+
+  private:
+    void updateWeight() override { prepared = false; }
+    void updateBias() override { prepared = false; }
+
+    void release()
+    {
+      if (handle) { oidnb200_conv_destroy(handle); handle = nullptr; }
+      if (packedWeight) { cudaFree(packedWeight); packedWeight = nullptr; }
+      if (packedBias) { cudaFree(packedBias); packedBias = nullptr; }
+    }
+
+    // ohwi fp16 host tensor [paddedO][3][3][paddedI] -> logical oihw rows appended to `out` ([O][Itotal][3][3])
+    static void gatherOIHW(const Tensor& w, int O, int Itotal, int iOffset, std::vector<uint16_t>& out)
+    {
+      const uint16_t* p = static_cast<const uint16_t*>(w.getPtr());
+      const int I = w.getI(), Ipad = w.getPaddedI();
+      for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I; ++i)
+          for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw)
+              out[(((size_t)o * Itotal + iOffset + i) * 3 + kh) * 3 + kw] = p[(((size_t)o * 3 + kh) * 3 + kw) * Ipad + i];
+    }
+
+    // creates the kernel-level op and uploads weights / bias in its packed layout (once per weight update)
+    void prepare()
+    {
+      if (prepared)
+        return;
+      release();
+      const B200Conv* first = partner ? partner : this;     // conv1 of a pair holds src1, W1 and the rank-1 bias
+      oidnb200_conv_desc d{};
+      d.H = srcDesc.getH(); d.W = srcDesc.getW();
+      d.C1 = first->srcDesc.getPaddedC();
+      d.C2 = partner ? srcDesc.getPaddedC() : 0;
+      d.Cout = weightDesc.getPaddedO();
+      d.relu = activation == Activation::ReLU;
+      d.post_op = postOp == PostOp::Pool ? 1 : 0;
+      d.src1_upsampled = 0;
+      d.shift_mode = 0;
+      checkKernel(oidnb200_conv_create(&d, &handle), "conv create");
+
+      const int O = weightDesc.getO();
+      const int I1 = first->weight->getI(), I2 = partner ? weight->getI() : 0;
+      std::vector<uint16_t> oihw((size_t)O * (I1 + I2) * 9);
+      gatherOIHW(*first->weight, O, I1 + I2, 0, oihw);
+      if (partner)
+        gatherOIHW(*weight, O, I1 + I2, I1, oihw);
+      std::vector<uint8_t> hostW(oidnb200_conv_weight_bytes(handle)), hostB(oidnb200_conv_bias_bytes(handle));
+      checkKernel(oidnb200_conv_pack_weights(handle, oihw.data(), O, I1, I2, hostW.data()), "conv weight reorder");
+      checkKernel(oidnb200_conv_pack_bias(handle, static_cast<const uint16_t*>(first->bias->getPtr()), O, hostB.data()),
+                  "conv bias reorder");
+      checkCuda(cudaMalloc(&packedWeight, hostW.size()));
+      checkCuda(cudaMalloc(&packedBias, hostB.size()));
+      checkCuda(cudaMemcpy(packedWeight, hostW.data(), hostW.size(), cudaMemcpyHostToDevice));
+      checkCuda(cudaMemcpy(packedBias, hostB.data(), hostB.size(), cudaMemcpyHostToDevice));
+      boundSrc1 = boundSrc2 = boundDst = nullptr;
+      prepared = true;
+    }
+
+    // tensor pointers move when the shared scratch heap is reallocated (Tensor::postRealloc): re-encode the TMA
+    // tensor maps whenever they differ from what is bound
+    void bind()
+    {
+      const void* s1 = partner ? partner->src->getPtr() : src->getPtr();
+      const void* s2 = partner ? src->getPtr() : nullptr;
+      void* d = dst->getPtr();
+      if (s1 == boundSrc1 && s2 == boundSrc2 && d == boundDst)
+        return;
+      checkKernel(oidnb200_conv_bind(handle, s1, s2, packedWeight, packedBias, d), "conv bind");
+      boundSrc1 = s1; boundSrc2 = s2; boundDst = d;
+    }
+
+    B200Engine* engine;
+    bool accumulate = false;
+    bool absorbed = false;
+    B200Conv* partner = nullptr;
+    bool prepared = false;
+    oidnb200_conv* handle = nullptr;
+    void* packedWeight = nullptr;
+    void* packedBias = nullptr;
+    const void* boundSrc1 = nullptr;
+    const void* boundSrc2 = nullptr;
+    void* boundDst = nullptr;
+  };
+
+  class B200Pool final : public Pool
+  {
+  public:
+    B200Pool(B200Engine* engine, const PoolDesc& desc) : Pool(desc), engine(engine) {}
+    Engine* getEngine() const override { return engine; }
+    void submitKernels(const Ref<CancellationToken>&) override
+    {
+      if (!src || !dst)
+        throw std::logic_error("pooling source/destination not set");
+      checkKernel(oidnb200_pool_launch(src->getPtr(), srcDesc.getH(), srcDesc.getW(), srcDesc.getPaddedC(), dst->getPtr(),
+                                       engine->getStream()), "pool");
+    }
+  private:
+    B200Engine* engine;
+  };
+
+  class B200Upsample final : public Upsample
+  {
+  public:
+    B200Upsample(B200Engine* engine, const UpsampleDesc& desc) : Upsample(desc), engine(engine) {}
+    Engine* getEngine() const override { return engine; }
+    void submitKernels(const Ref<CancellationToken>&) override
+    {
+      if (!src || !dst)
+        throw std::logic_error("upsampling source/destination not set");
+      checkKernel(oidnb200_upsample_launch(src->getPtr(), srcDesc.getH(), srcDesc.getW(), srcDesc.getPaddedC(), dst->getPtr(),
+                                           engine->getStream()), "upsample");
+    }
+  private:
+    B200Engine* engine;
+  };
+
+  class B200InputProcess final : public InputProcess
+  {
+  public:
+    B200InputProcess(B200Engine* engine, const InputProcessDesc& desc) : InputProcess(engine, desc), engine(engine) {}
+    Engine* getEngine() const override { return engine; }
+    void submitKernels(const Ref<CancellationToken>&) override
+    {
+      check();
+      // the kernel ABI's first image is the main input: color, else albedo, else normal (InputProcess::getMainSrc)
+      const oidnb200_image none = toABI(Ref<Image>());
+      oidnb200_image c = toABI(color), a = toABI(albedo), n = toABI(normal);
+      if (!color)
+      {
+        c = albedo ? a : n;
+        a = n = none;
+      }
+      const oidnb200_tile t = toABI(tile);
+      const oidnb200_transfer tf = toABI(*transferFunc);
+      checkKernel(oidnb200_input_process_launch(&c, &a, &n, &t, &tf, hdr, snorm, dst->getPtr(), dstDesc.getH(),
+                                                dstDesc.getW(), dstDesc.getPaddedC(), engine->getStream()), "input process");
+    }
+  private:
+    B200Engine* engine;
+  };
+
+  class B200OutputProcess final : public OutputProcess
+  {
+  public:
+    B200OutputProcess(B200Engine* engine, const OutputProcessDesc& desc) : OutputProcess(desc), engine(engine) {}
+    Engine* getEngine() const override { return engine; }
+    void submitKernels(const Ref<CancellationToken>&) override
+    {
+      check();
+      const oidnb200_image d = toABI(dst);
+      const oidnb200_tile t = toABI(tile);
+      const oidnb200_transfer tf = toABI(*transferFunc);
+      checkKernel(oidnb200_output_process_launch(src->getPtr(), srcDesc.getH(), srcDesc.getW(), srcDesc.getPaddedC(), &t, &tf,
+                                                 hdr, snorm, &d, engine->getStream()), "output process");
+    }
+  private:
+    B200Engine* engine;
+  };
+
+  class B200Autoexposure final : public Autoexposure
+  {
+  public:
+    B200Autoexposure(B200Engine* engine, const ImageDesc& srcDesc) : Autoexposure(srcDesc), engine(engine) {}
+    Engine* getEngine() const override { return engine; }
+    size_t getScratchByteSize() override { return oidnb200_autoexposure_scratch_bytes(srcDesc.getH(), srcDesc.getW()); }
+    void setScratch(const Ref<Buffer>& buffer) override { scratch = buffer; }
+    void submitKernels(const Ref<CancellationToken>&) override
+    {
+      if (!src || !dst || !scratch)
+        throw std::logic_error("autoexposure source/destination/scratch not set");
+      const oidnb200_image s = toABI(src);
+      checkKernel(oidnb200_autoexposure_launch(&s, scratch->getPtr(), getDstPtr(), engine->getStream()), "autoexposure");
+    }
+  private:
+    B200Engine* engine;
+    Ref<Buffer> scratch;
+  };
+
+  class B200ImageCopy final : public ImageCopy
+  {
+  public:
+    explicit B200ImageCopy(B200Engine* engine) : engine(engine) {}
+    Engine* getEngine() const override { return engine; }
+    void submitKernels(const Ref<CancellationToken>&) override
+    {
+      check();
+      const oidnb200_image s = toABI(src), d = toABI(dst);
+      checkKernel(oidnb200_image_copy_launch(&s, &d, engine->getStream()), "image copy");
+    }
+  private:
+    B200Engine* engine;
+  };
+
+  Ref<Conv> B200Engine::newConv(const ConvDesc& desc) { return makeRef<B200Conv>(this, desc); }
+  Ref<Pool> B200Engine::newPool(const PoolDesc& desc) { return makeRef<B200Pool>(this, desc); }
+  Ref<Upsample> B200Engine::newUpsample(const UpsampleDesc& desc) { return makeRef<B200Upsample>(this, desc); }
+  Ref<Autoexposure> B200Engine::newAutoexposure(const ImageDesc& srcDesc) { return makeRef<B200Autoexposure>(this, srcDesc); }
+  Ref<InputProcess> B200Engine::newInputProcess(const InputProcessDesc& desc) { return makeRef<B200InputProcess>(this, desc); }
+  Ref<OutputProcess> B200Engine::newOutputProcess(const OutputProcessDesc& desc) { return makeRef<B200OutputProcess>(this, desc); }
+  Ref<ImageCopy> B200Engine::newImageCopy() { return makeRef<B200ImageCopy>(this); }
+#endif // OIDN_B200_OP_LEVEL
 
   class B200DeviceFactory final : public CUDADeviceFactoryBase
   {

@@ -35,4 +35,28 @@ cp $BLD/libOpenImageDenoise_device_cuda.so.2.4.1 "$OUT/lib/"; ln -sf libOpenImag
 cp "$ROOT/oidn_b200/liboidn_b200.so" "$OUT/lib/"
 cp $BLD/oidnBenchmark $BLD/oidnTest $BLD/oidnDenoise "$OUT/bin/"
 cp $SRC/weights/*.tza "$OUT/weights/"
-echo "integration build installed in $OUT"
+echo "integration build (filter-level module, core with the one-word change) installed in $OUT"
+
+# Op-level variant (-DOIDN_B200_OP_LEVEL): NO core change, so it is linked against the UNMODIFIED reference build of
+# tools/build_reference_cuda.sh (/tmp/oidn_build) and only replaces that build's CUDA device module. The reference's
+# own filters, graph, arena planner and tile loop drive this backend's ops; built-in weights are the core's blobs.
+OPS="$ROOT/baseline/_b200_ops"; REFBLD=/tmp/oidn_build
+[ -f $REFBLD/libOpenImageDenoise_core.so.2.4.1 ] || bash "$ROOT/tools/build_reference_cuda.sh"
+rm -rf "$OPS"; mkdir -p "$OPS/lib" "$OPS/bin"
+$CXX -std=c++17 -O2 -fPIC -fvisibility=hidden -fvisibility-inlines-hidden -Wall -Wno-unknown-pragmas \
+     -D__STDC_CONSTANT_MACROS -D__STDC_LIMIT_MACROS -DOIDN_B200_OP_LEVEL \
+     -I/usr/local/cuda/targets/x86_64-linux/include -I"$ROOT/include" -isystem /tmp/oidn_ref -isystem /tmp/oidn_ref/external -isystem $REFBLD \
+     -shared -Wl,-soname,libOpenImageDenoise_device_cuda.so.2.4.1 -Wl,-z,now \
+     -o "$OPS/lib/libOpenImageDenoise_device_cuda.so.2.4.1" "$ROOT/integration/b200_module.cpp" \
+     $REFBLD/libOpenImageDenoise_core.so.2.4.1 -L"$ROOT/oidn_b200" -loidn_b200 \
+     -L/usr/local/cuda/targets/x86_64-linux/lib -lcudart_static -lrt -lpthread -ldl \
+     -Wl,-rpath,'$ORIGIN'
+ln -sf libOpenImageDenoise_device_cuda.so.2.4.1 "$OPS/lib/libOpenImageDenoise_device_cuda.so"
+for f in libOpenImageDenoise.so libOpenImageDenoise.so.2 libOpenImageDenoise.so.2.4.1 libOpenImageDenoise_core.so libOpenImageDenoise_core.so.2.4.1; do
+  cp -al "$ROOT/baseline/_ref/lib/$f" "$OPS/lib/" 2>/dev/null || cp -a "$ROOT/baseline/_ref/lib/$f" "$OPS/lib/"
+done
+for f in oidnBenchmark oidnTest oidnDenoise; do
+  cp -al "$ROOT/baseline/_ref/bin/$f" "$OPS/bin/" 2>/dev/null || cp -a "$ROOT/baseline/_ref/bin/$f" "$OPS/bin/"
+done
+cp "$ROOT/oidn_b200/liboidn_b200.so" "$OPS/lib/"
+echo "op-level module (unmodified reference core) installed in $OPS"
