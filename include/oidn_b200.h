@@ -43,9 +43,12 @@ typedef bool (*OIDNB200ProgressMonitorFunction)(void* userPtr, double n); /* oid
 /* oidnGetNumPhysicalDevices restricted to B200-class GPUs (oidn.h:55). */
 OIDNB200_API int oidnb200GetNumPhysicalDevices(void);
 /* oidnNewCUDADevice(deviceIDs, streams, numPairs) (oidn.h:152-153). streams may be NULL or hold
- * NULL entries (the engine creates its own stream). numPairs > 1 makes a multi-GPU device whose
- * tiles are dealt round-robin to the GPUs; all GPUs must be peer accessible. Returns NULL on error
- * (fetch it with oidnb200GetDeviceError(NULL, ...)). */
+ * NULL entries (the engine creates its own stream). numPairs > 1 makes a multi-engine device whose
+ * tiles are dealt round-robin to the (GPU, stream) pairs (core/unet_filter.cpp:219); distinct GPUs must
+ * be peer accessible; the same GPU may appear in several pairs. A frame that does not live in the memory
+ * of the GPU that runs a tile (pinned host memory, another GPU) is staged tile by tile with copy engines
+ * (device parameter "staging": -1 auto (default), 0 never, 1 always; see oidn_b200/csrc/host/filter.hpp).
+ * Returns NULL on error (fetch it with oidnb200GetDeviceError(NULL, ...)). */
 OIDNB200_API OIDNB200Device oidnb200NewCUDADevice(const int* deviceIDs, void* const* streams, int numPairs);
 /* oidnNewDevice(OIDN_DEVICE_TYPE_CUDA) (oidn.h:128): GPU 0, own stream. */
 OIDNB200_API OIDNB200Device oidnb200NewDevice(void);
@@ -83,6 +86,21 @@ OIDNB200_API void oidnb200CopyRectAsync(OIDNB200Device device, void* dst, size_t
 OIDNB200_API void oidnb200GetBufferIpcHandle(OIDNB200Buffer buffer, void* outHandle64);
 OIDNB200_API OIDNB200Buffer oidnb200NewSharedBufferFromIpcHandle(OIDNB200Device device, const void* handle64, size_t byteSize);
 
+/* oidnNewSharedBufferFromFD (oidn.h:326-329; devices/cuda/cuda_external_buffer.cpp:9-23, :66-84): imports device
+ * memory from a POSIX file descriptor. fdType uses OIDNExternalMemoryTypeFlag's numbering (oidn.h:296-311); like the
+ * reference CUDA device only OPAQUE_FD is supported, DMA_BUF is rejected with InvalidArgument. The fd is tried as an
+ * external-memory object of another API first (cudaImportExternalMemory, what a Vulkan / OpenGL renderer exports),
+ * then as a CUDA allocation exported with cuMemExportToShareableHandle (another CUDA process, or
+ * oidnb200GetBufferFD below). On success the buffer owns the fd. */
+enum { OIDNB200_EXTERNAL_MEMORY_TYPE_FLAG_NONE = 0, OIDNB200_EXTERNAL_MEMORY_TYPE_FLAG_OPAQUE_FD = 1 << 0,
+       OIDNB200_EXTERNAL_MEMORY_TYPE_FLAG_DMA_BUF = 1 << 1 };
+OIDNB200_API OIDNB200Buffer oidnb200NewSharedBufferFromFD(OIDNB200Device device, int fdType, int fd, size_t byteSize);
+/* Producer side of the same interop (no counterpart in oidn.h, where the renderer's API exports): a device buffer
+ * whose memory can be handed to another process or API as an opaque fd. oidnb200GetBufferFD returns a new fd per
+ * call (the caller owns it; -1 on error). */
+OIDNB200_API OIDNB200Buffer oidnb200NewExportableBuffer(OIDNB200Device device, size_t byteSize);
+OIDNB200_API int oidnb200GetBufferFD(OIDNB200Buffer buffer);
+
 /* ---- filters ------------------------------------------------------------------------------ */
 OIDNB200_API OIDNB200Filter oidnb200NewFilter(OIDNB200Device device, const char* type); /* "RT" | "RTLightmap", oidn.h:392 */
 OIDNB200_API void oidnb200RetainFilter(OIDNB200Filter filter);
@@ -114,6 +132,7 @@ OIDNB200_API void oidnb200ExecuteFilterAsync(OIDNB200Filter filter);  /* oidn.h:
 typedef struct oidnb200_filter_info
 {
   int tileH, tileW, tileCountH, tileCountW, tileOverlap, tileAlignment, largeModel, numOps;
+  int staged; /* 1: the last frame ran through the tile-staging pipeline (device parameter "staging") */
   size_t memoryBytes;
 } oidnb200_filter_info;
 OIDNB200_API void oidnb200GetFilterInfo(OIDNB200Filter filter, oidnb200_filter_info* info);

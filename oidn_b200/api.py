@@ -46,6 +46,8 @@ class Device:
     st = None
     if streams is not None:
       st = (C.c_void_p * len(device_ids))(*[int(s) if s else None for s in streams])
+    self.device_ids = tuple(device_ids)
+    self.streams = tuple(int(s) if s else None for s in streams) if streams is not None else None
     self._h = capi.lib().oidnb200NewCUDADevice(ids, st, len(device_ids))
     if not self._h:
       _check(None)
@@ -92,6 +94,16 @@ class Device:
     h = capi.lib().oidnb200NewSharedBufferFromIpcHandle(self._h, raw, byte_size); _check(self._h)
     return Buffer(self, h)
 
+  def new_exportable_buffer(self, byte_size):
+    """Device buffer whose memory can be exported as an opaque fd (Buffer.fd())."""
+    h = capi.lib().oidnb200NewExportableBuffer(self._h, byte_size); _check(self._h)
+    return Buffer(self, h)
+
+  def import_fd(self, fd, byte_size, fd_type=capi.EXTERNAL_MEMORY_OPAQUE_FD):
+    """oidnNewSharedBufferFromFD: the buffer owns the fd on success."""
+    h = capi.lib().oidnb200NewSharedBufferFromFD(self._h, fd_type, fd, byte_size); _check(self._h)
+    return Buffer(self, h)
+
   def release(self):
     if self._h:
       capi.lib().oidnb200ReleaseDevice(self._h)
@@ -120,6 +132,10 @@ class Buffer:
     raw = (C.c_char * 64)()
     capi.lib().oidnb200GetBufferIpcHandle(self._h, raw); _check(self.device._h)
     return bytes(raw)
+
+  def fd(self):
+    fd = capi.lib().oidnb200GetBufferFD(self._h); _check(self.device._h)
+    return fd
 
   def write(self, array, byte_offset=0, sync=True):
     a = np.ascontiguousarray(array)

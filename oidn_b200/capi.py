@@ -12,6 +12,7 @@ QUALITY_DEFAULT, QUALITY_FAST, QUALITY_BALANCED, QUALITY_HIGH = 0, 4, 5, 6
 STORAGE_UNDEFINED, STORAGE_HOST, STORAGE_DEVICE, STORAGE_MANAGED = 0, 1, 2, 3
 (ERROR_NONE, ERROR_UNKNOWN, ERROR_INVALID_ARGUMENT, ERROR_INVALID_OPERATION, ERROR_OUT_OF_MEMORY,
  ERROR_UNSUPPORTED_HARDWARE, ERROR_CANCELLED) = range(7)
+EXTERNAL_MEMORY_OPAQUE_FD, EXTERNAL_MEMORY_DMA_BUF = 1, 2
 TF_LINEAR, TF_SRGB, TF_PU, TF_LOG = 0, 1, 2, 3
 
 
@@ -39,7 +40,7 @@ class Transfer(C.Structure):
 
 class FilterInfo(C.Structure):
   _fields_ = [(n, C.c_int) for n in ("tileH", "tileW", "tileCountH", "tileCountW", "tileOverlap", "tileAlignment",
-                                     "largeModel", "numOps")] + [("memoryBytes", C.c_size_t)]
+                                     "largeModel", "numOps", "staged")] + [("memoryBytes", C.c_size_t)]
 
 
 class OpTime(C.Structure):
@@ -109,6 +110,9 @@ FILTER_ABI = {
   "oidnb200CopyRectAsync": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
   "oidnb200GetBufferIpcHandle": (None, [C.c_void_p, C.c_void_p]),
   "oidnb200NewSharedBufferFromIpcHandle": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_size_t]),
+  "oidnb200NewSharedBufferFromFD": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
+  "oidnb200NewExportableBuffer": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+  "oidnb200GetBufferFD": (C.c_int, [C.c_void_p]),
   "oidnb200NewFilter": (C.c_void_p, [C.c_void_p, C.c_char_p]),
   "oidnb200RetainFilter": (None, [C.c_void_p]),
   "oidnb200ReleaseFilter": (None, [C.c_void_p]),

@@ -4,8 +4,11 @@
 #include "../../../include/oidn_b200.h"
 #include "filter.hpp"
 #include <atomic>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstring>
+#include <unistd.h>
+#include <map>
 
 using namespace oidnb200;
 
@@ -23,6 +26,11 @@ struct oidnb200_buffer_t
   size_t size = 0;
   Storage storage = Storage::Device;
   bool imported = false; // opened from a CUDA IPC handle
+  // external memory (oidnb200NewSharedBufferFromFD) and exportable memory (oidnb200NewExportableBuffer)
+  enum Kind { Plain, External, Vmm } kind = Plain;
+  cudaExternalMemory_t ext = nullptr;         // External: imported with cudaImportExternalMemory
+  unsigned long long vmmHandle = 0;           // Vmm: CUmemGenericAllocationHandle (created or imported)
+  size_t vmmSize = 0;                         // Vmm: mapped (granularity-rounded) size
 };
 
 struct oidnb200_filter_t
@@ -30,6 +38,9 @@ struct oidnb200_filter_t
   std::atomic<int> refs{1};
   oidnb200_device_t* device;
   std::shared_ptr<Filter> impl;
+  // buffers behind the images set with oidnb200SetFilterImage: the filter keeps them alive as the reference's
+  // Image holds a Ref<Buffer> (core/image.h), so releasing a buffer after setting it is legal
+  std::map<std::string, oidnb200_buffer_t*> buffers;
 };
 
 namespace {
@@ -62,6 +73,126 @@ void releaseDevice(oidnb200_device_t* d)
     try { if (d->impl && d->impl->isCommitted()) d->impl->wait(); } catch (...) {}
     delete d;
   }
+}
+
+// CUDA virtual-memory-management entry points (driver API, resolved at run time: the library links only the
+// static runtime). Used for device memory that can be exported as / imported from an opaque POSIX fd.
+struct VmmApi
+{
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*addrFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*setAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*exportHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*importHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+  CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+
+const VmmApi& vmmApi()
+{
+  static VmmApi api;
+  static bool tried = false;
+  if (!tried)
+  {
+    tried = true;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    api.ok = get("cuMemCreate", (void**)&api.create) && get("cuMemRelease", (void**)&api.release) &&
+             get("cuMemAddressReserve", (void**)&api.reserve) && get("cuMemAddressFree", (void**)&api.addrFree) &&
+             get("cuMemMap", (void**)&api.map) && get("cuMemUnmap", (void**)&api.unmap) &&
+             get("cuMemSetAccess", (void**)&api.setAccess) && get("cuMemExportToShareableHandle", (void**)&api.exportHandle) &&
+             get("cuMemImportFromShareableHandle", (void**)&api.importHandle) &&
+             get("cuMemGetAllocationGranularity", (void**)&api.granularity);
+    cudaGetLastError();
+  }
+  return api;
+}
+
+void checkCu(CUresult r, const char* what)
+{
+  if (r == CUDA_SUCCESS) return;
+  if (r == CUDA_ERROR_OUT_OF_MEMORY) throw Exception(Error::OutOfMemory, std::string(what) + ": out of memory");
+  throw Exception(Error::Unknown, std::string(what) + ": CUDA driver error " + std::to_string((int)r));
+}
+
+CUmemAllocationProp vmmProp(int deviceID)
+{
+  CUmemAllocationProp prop{};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = deviceID;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  return prop;
+}
+
+// Maps a VMM allocation handle into this process's address space with read/write access for the device.
+void* vmmMapHandle(CUmemGenericAllocationHandle h, size_t size, int deviceID)
+{
+  const VmmApi& v = vmmApi();
+  CUdeviceptr va = 0;
+  checkCu(v.reserve(&va, size, 0, 0, 0), "cuMemAddressReserve");
+  CUresult r = v.map(va, size, 0, h, 0);
+  if (r == CUDA_SUCCESS)
+  {
+    CUmemAccessDesc acc{};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE; acc.location.id = deviceID;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    r = v.setAccess(va, size, &acc, 1);
+    if (r != CUDA_SUCCESS) v.unmap(va, size);
+  }
+  if (r != CUDA_SUCCESS) { v.addrFree(va, size); checkCu(r, "cuMemMap"); }
+  return reinterpret_cast<void*>(va);
+}
+
+// Frees the buffer's memory; the device mutex is held by the caller.
+void destroyBufferLocked(oidnb200_buffer_t* b)
+{
+  Device* dev = b->device->impl.get();
+  dev->wait();
+  if (b->kind == oidnb200_buffer_t::External)
+  {
+    dev->getEngine(0)->makeCurrent();
+    cudaFree(b->ptr);                       // devices/cuda/cuda_external_buffer.cpp:86-90
+    cudaDestroyExternalMemory(b->ext);
+  }
+  else if (b->kind == oidnb200_buffer_t::Vmm)
+  {
+    dev->getEngine(0)->makeCurrent();
+    const VmmApi& v = vmmApi();
+    v.unmap((CUdeviceptr)b->ptr, b->vmmSize);
+    v.addrFree((CUdeviceptr)b->ptr, b->vmmSize);
+    v.release(b->vmmHandle);
+  }
+  else if (b->imported) { dev->getEngine(0)->makeCurrent(); cudaIpcCloseMemHandle(b->ptr); }
+  else if (b->storage == Storage::Host) dev->freeHost(b->ptr);
+  else dev->getEngine(0)->free(b->ptr, b->storage);
+}
+
+// Drops a reference held by a filter (device mutex held; the filter's own device reference keeps the device alive).
+void dropBufferLocked(oidnb200_buffer_t* b)
+{
+  if (b && b->refs.fetch_sub(1) == 1)
+  {
+    oidnb200_device_t* d = b->device;
+    try { destroyBufferLocked(b); } catch (...) {}
+    delete b;
+    d->refs.fetch_sub(1);
+  }
+}
+
+void holdBuffer(oidnb200_filter_t* f, const std::string& name, oidnb200_buffer_t* b)
+{
+  if (b) b->refs.fetch_add(1);
+  auto it = f->buffers.find(name);
+  oidnb200_buffer_t* old = it == f->buffers.end() ? nullptr : it->second;
+  if (b) f->buffers[name] = b; else if (it != f->buffers.end()) f->buffers.erase(it);
+  dropBufferLocked(old);
 }
 
 void checkString(const char* s)
@@ -160,7 +291,7 @@ OIDNB200Buffer oidnb200NewBufferWithStorage(OIDNB200Device d, size_t byteSize, i
     const Storage s = static_cast<Storage>(storage);
     if (s != Storage::Host && s != Storage::Device && s != Storage::Managed)
       throw Exception(Error::InvalidArgument, "invalid storage mode");
-    void* p = d->impl->getEngine(0)->malloc(byteSize, s);
+    void* p = s == Storage::Host ? d->impl->allocHost(byteSize) : d->impl->getEngine(0)->malloc(byteSize, s);
     b = new oidnb200_buffer_t();
     b->device = d; b->ptr = p; b->size = byteSize; b->storage = s;
     retainDevice(d);
@@ -183,6 +314,7 @@ static void bufferCopy(oidnb200_buffer_t* b, size_t off, size_t n, void* dst, co
     if (off + n > b->size || off + n < off) throw Exception(Error::InvalidArgument, "buffer region is out of bounds");
     if (n == 0) return;
     if ((read && !dst) || (!read && !src)) throw Exception(Error::InvalidArgument, "host pointer is null");
+    b->device->impl->joinStaged();
     Engine* e = b->device->impl->getEngine(0);
     uint8_t* p = static_cast<uint8_t*>(b->ptr) + off;
     if (read) e->submitCopy(dst, p, n); else e->submitCopy(p, src, n);
@@ -203,6 +335,7 @@ void oidnb200CopyRectAsync(OIDNB200Device d, void* dst, size_t dstPitch, const v
     if (widthBytes == 0 || height == 0) return;
     if (!dst || !src) throw Exception(Error::InvalidArgument, "pointer is null");
     if (dstPitch < widthBytes || srcPitch < widthBytes) throw Exception(Error::InvalidArgument, "pitch is smaller than the row");
+    d->impl->joinStaged();
     d->impl->getEngine(0)->submitCopy2D(dst, dstPitch, src, srcPitch, widthBytes, height);
   });
 }
@@ -213,11 +346,7 @@ void oidnb200ReleaseBuffer(OIDNB200Buffer b)
   if (b->refs.fetch_sub(1) == 1)
   {
     oidnb200_device_t* d = b->device;
-    guarded(d, [&] {
-      d->impl->wait();
-      if (b->imported) { d->impl->getEngine(0)->makeCurrent(); cudaIpcCloseMemHandle(b->ptr); }
-      else d->impl->getEngine(0)->free(b->ptr, b->storage);
-    });
+    guarded(d, [&] { destroyBufferLocked(b); });
     delete b;
     releaseDevice(d);
   }
@@ -228,7 +357,7 @@ void oidnb200GetBufferIpcHandle(OIDNB200Buffer b, void* outHandle64)
   if (!b) return;
   guarded(b->device, [&] {
     if (!outHandle64) throw Exception(Error::InvalidArgument, "handle pointer is null");
-    if (b->storage != Storage::Device || b->imported)
+    if (b->storage != Storage::Device || b->imported || b->kind != oidnb200_buffer_t::Plain)
       throw Exception(Error::InvalidOperation, "only device-storage buffers owned by this process can be exported");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     cudaIpcMemHandle_t h;
@@ -256,6 +385,100 @@ OIDNB200Buffer oidnb200NewSharedBufferFromIpcHandle(OIDNB200Device d, const void
   return b;
 }
 
+OIDNB200Buffer oidnb200NewSharedBufferFromFD(OIDNB200Device d, int fdType, int fd, size_t byteSize)
+{
+  oidnb200_buffer_t* b = nullptr;
+  guarded(d, [&] {
+    d->impl->checkCommitted();
+    // the CUDA device supports opaque fds only (devices/cuda/cuda_external_buffer.cpp:13-14, api/api.cpp:603-604)
+    if (fdType != OIDNB200_EXTERNAL_MEMORY_TYPE_FLAG_OPAQUE_FD)
+      throw Exception(Error::InvalidArgument, "external memory type not supported by the device");
+    if (fd < 0 || byteSize == 0) throw Exception(Error::InvalidArgument, "invalid file descriptor or size");
+    Engine* e = d->impl->getEngine(0);
+    e->makeCurrent();
+    // 1. an external-memory object of another API (Vulkan, ...): cudaImportExternalMemory owns the fd on success
+    cudaExternalMemoryHandleDesc hd{};
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    hd.size = byteSize;
+    cudaExternalMemory_t ext = nullptr;
+    if (cudaImportExternalMemory(&ext, &hd) == cudaSuccess)
+    {
+      void* p = nullptr;
+      cudaExternalMemoryBufferDesc bd{};
+      bd.offset = 0; bd.size = byteSize; bd.flags = 0;
+      const cudaError_t me = cudaExternalMemoryGetMappedBuffer(&p, ext, &bd);
+      if (me != cudaSuccess) { cudaDestroyExternalMemory(ext); checkCuda(me, "cudaExternalMemoryGetMappedBuffer"); }
+      b = new oidnb200_buffer_t();
+      b->device = d; b->ptr = p; b->size = byteSize; b->storage = Storage::Device;
+      b->kind = oidnb200_buffer_t::External; b->ext = ext;
+      retainDevice(d);
+      return;
+    }
+    cudaGetLastError();
+    // 2. a CUDA allocation exported with cuMemExportToShareableHandle (oidnb200GetBufferFD, another CUDA process)
+    const VmmApi& v = vmmApi();
+    if (!v.ok) throw Exception(Error::InvalidArgument, "the file descriptor is not an importable memory object");
+    CUmemGenericAllocationHandle h = 0;
+    if (v.importHandle(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS)
+      throw Exception(Error::InvalidArgument, "the file descriptor is not an importable memory object");
+    size_t gran = 0;
+    const CUmemAllocationProp prop = vmmProp(e->getDeviceID());
+    checkCu(v.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM), "cuMemGetAllocationGranularity");
+    const size_t mapped = round_up(byteSize, gran);
+    void* p = nullptr;
+    try { p = vmmMapHandle(h, mapped, e->getDeviceID()); }
+    catch (...) { v.release(h); throw; }
+    close(fd); // ownership passes to the buffer, as with cudaImportExternalMemory
+    b = new oidnb200_buffer_t();
+    b->device = d; b->ptr = p; b->size = byteSize; b->storage = Storage::Device;
+    b->kind = oidnb200_buffer_t::Vmm; b->vmmHandle = h; b->vmmSize = mapped;
+    retainDevice(d);
+  });
+  return b;
+}
+
+OIDNB200Buffer oidnb200NewExportableBuffer(OIDNB200Device d, size_t byteSize)
+{
+  oidnb200_buffer_t* b = nullptr;
+  guarded(d, [&] {
+    d->impl->checkCommitted();
+    if (byteSize == 0) throw Exception(Error::InvalidArgument, "buffer size is zero");
+    const VmmApi& v = vmmApi();
+    if (!v.ok) throw Exception(Error::UnsupportedHardware, "CUDA virtual memory management is not available");
+    Engine* e = d->impl->getEngine(0);
+    e->makeCurrent();
+    cudaFree(nullptr); // the primary context must exist before driver-API calls
+    const CUmemAllocationProp prop = vmmProp(e->getDeviceID());
+    size_t gran = 0;
+    checkCu(v.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM), "cuMemGetAllocationGranularity");
+    const size_t mapped = round_up(byteSize, gran);
+    CUmemGenericAllocationHandle h = 0;
+    checkCu(v.create(&h, mapped, &prop, 0), "cuMemCreate");
+    void* p = nullptr;
+    try { p = vmmMapHandle(h, mapped, e->getDeviceID()); }
+    catch (...) { v.release(h); throw; }
+    b = new oidnb200_buffer_t();
+    b->device = d; b->ptr = p; b->size = byteSize; b->storage = Storage::Device;
+    b->kind = oidnb200_buffer_t::Vmm; b->vmmHandle = h; b->vmmSize = mapped;
+    retainDevice(d);
+  });
+  return b;
+}
+
+int oidnb200GetBufferFD(OIDNB200Buffer b)
+{
+  int fd = -1;
+  if (!b) return fd;
+  guarded(b->device, [&] {
+    if (b->kind != oidnb200_buffer_t::Vmm)
+      throw Exception(Error::InvalidOperation, "only buffers created with oidnb200NewExportableBuffer can be exported");
+    b->device->impl->getEngine(0)->makeCurrent();
+    checkCu(vmmApi().exportHandle(&fd, b->vmmHandle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0), "cuMemExportToShareableHandle");
+  });
+  return fd;
+}
+
 // ---- filters ----------------------------------------------------------------------------------
 OIDNB200Filter oidnb200NewFilter(OIDNB200Device d, const char* type)
 {
@@ -278,7 +501,11 @@ void oidnb200ReleaseFilter(OIDNB200Filter f)
   if (f->refs.fetch_sub(1) == 1)
   {
     oidnb200_device_t* d = f->device;
-    guarded(d, [&] { d->impl->wait(); f->impl.reset(); }); // api/api.cpp:111-141: wait for idle, then destroy
+    guarded(d, [&] {
+      d->impl->wait(); f->impl.reset(); // api/api.cpp:111-141: wait for idle, then destroy
+      for (auto& kv : f->buffers) dropBufferLocked(kv.second);
+      f->buffers.clear();
+    });
     delete f;
     releaseDevice(d);
   }
@@ -295,6 +522,7 @@ void oidnb200SetFilterImage(OIDNB200Filter f, const char* name, OIDNB200Buffer b
     if (im && im.end() > static_cast<uint8_t*>(buffer->ptr) + buffer->size)
       throw Exception(Error::InvalidArgument, "buffer region is out of bounds");
     f->impl->setImage(name, im);
+    holdBuffer(f, name, im ? buffer : nullptr);
   });
 }
 
@@ -305,12 +533,13 @@ void oidnb200SetSharedFilterImage(OIDNB200Filter f, const char* name, void* devP
   guarded(f->device, [&] {
     checkString(name);
     f->impl->setImage(name, makeImage(devPtr, format, width, height, byteOffset, pixelByteStride, rowByteStride));
+    holdBuffer(f, name, nullptr);
   });
 }
 
 void oidnb200UnsetFilterImage(OIDNB200Filter f, const char* name)
 {
-  if (f) guarded(f->device, [&] { checkString(name); f->impl->unsetImage(name); });
+  if (f) guarded(f->device, [&] { checkString(name); f->impl->unsetImage(name); holdBuffer(f, name, nullptr); });
 }
 
 void oidnb200SetSharedFilterData(OIDNB200Filter f, const char* name, void* hostPtr, size_t byteSize)
@@ -392,6 +621,7 @@ void oidnb200GetFilterInfo(OIDNB200Filter f, oidnb200_filter_info* info)
     info->tileOverlap = p.tileOverlap; info->tileAlignment = p.tileAlignment;
     info->largeModel = u->isLargeModel();
     info->numOps = u->getNumOps();
+    info->staged = u->wasStaged();
     info->memoryBytes = u->getScratchByteSize();
   });
 }

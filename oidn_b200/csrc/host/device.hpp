@@ -6,6 +6,7 @@
 // submitBarrier() is an event join across the engines' streams.
 #pragma once
 #include "engine.hpp"
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -31,6 +32,11 @@ public:
   // engine 0 waits for every engine, then every engine waits for engine 0
   void submitBarrier();
   void wait(); // block until every stream is idle
+  // Staged frames (UNetFilter::submitFrameStaged) finish on the engines' copy-out streams: deferJoin() notes the
+  // events that mark their end, joinStaged() makes every main stream wait for them. Called before anything else
+  // is enqueued on a main stream (buffer copies, in-place frames) and by a caller-supplied stream's frames.
+  void deferJoin(const std::vector<void*>& endEvents) { pendingJoin = endEvents; }
+  void joinStaged();
 
   std::shared_ptr<Filter> newFilter(const std::string& type);
 
@@ -55,11 +61,18 @@ public:
 
   std::mutex& getMutex() { return mutex; }
 
+  // Pinned host memory for buffers with host storage. On a multi-GPU device the pages are interleaved over the
+  // host's NUMA nodes (mbind) before they are page-locked, so the GPUs of both sockets pull their tiles of a
+  // frame from local and remote memory alike instead of all crossing to the socket that first touched it.
+  void* allocHost(size_t bytes);
+  void freeHost(void* ptr);
+
 private:
   std::vector<int> deviceIDs;
   std::vector<void*> userStreams;
   std::vector<std::unique_ptr<Engine>> engines;
   std::vector<void*> events; // one cudaEvent_t per engine
+  std::vector<void*> pendingJoin;
   bool committed = false;
   int verbose = 0;
   int profile = 0;
@@ -67,6 +80,8 @@ private:
   int tilePolicy = 1;
   int fuseOutput = 1;
   int graph = 0;
+  int staging = -1;
+  std::map<void*, size_t> hostMaps; // interleaved host allocations (mmap + cudaHostRegister): ptr -> bytes
   std::string weightsDir;
   std::mutex mutex;
   Error errorCode = Error::None;

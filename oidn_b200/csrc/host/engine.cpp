@@ -47,11 +47,32 @@ Engine::Engine(int deviceID, void* userStream) : deviceID(deviceID)
 
 Engine::~Engine()
 {
-  if (ownStream && stream)
+  cudaSetDevice(deviceID);
+  for (void* e : events) cudaEventDestroy(static_cast<cudaEvent_t>(e));
+  for (void* s : aux)
+    if (s) cudaStreamDestroy(static_cast<cudaStream_t>(s));
+  if (ownStream && stream) cudaStreamDestroy(static_cast<cudaStream_t>(stream));
+}
+
+void* Engine::getAuxStream(AuxStream which)
+{
+  if (!aux[which])
   {
-    cudaSetDevice(deviceID);
-    cudaStreamDestroy(static_cast<cudaStream_t>(stream));
+    makeCurrent();
+    cudaStream_t s;
+    checkCuda(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+    aux[which] = s;
   }
+  return aux[which];
+}
+
+void* Engine::newEvent()
+{
+  makeCurrent();
+  cudaEvent_t e;
+  checkCuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+  events.push_back(e);
+  return e;
 }
 
 void Engine::makeCurrent() const { checkCuda(cudaSetDevice(deviceID), "cudaSetDevice"); }
@@ -81,14 +102,14 @@ void Engine::free(void* ptr, Storage storage)
 void Engine::submitCopy(void* dst, const void* src, size_t bytes)
 {
   makeCurrent();
-  checkCuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)), "cudaMemcpyAsync");
+  checkCuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(getStream())), "cudaMemcpyAsync");
 }
 
 void Engine::submitCopy2D(void* dst, size_t dstPitch, const void* src, size_t srcPitch, size_t widthBytes, size_t height)
 {
   makeCurrent();
   checkCuda(cudaMemcpy2DAsync(dst, dstPitch, src, srcPitch, widthBytes, height, cudaMemcpyDefault,
-                              static_cast<cudaStream_t>(stream)), "cudaMemcpy2DAsync");
+                              static_cast<cudaStream_t>(getStream())), "cudaMemcpy2DAsync");
 }
 
 static void CUDART_CB hostFuncTrampoline(void* p)
@@ -101,13 +122,15 @@ void Engine::submitHostFunc(std::function<void()>&& f)
 {
   makeCurrent();
   auto* heap = new std::function<void()>(std::move(f));
-  checkCuda(cudaLaunchHostFunc(static_cast<cudaStream_t>(stream), hostFuncTrampoline, heap), "cudaLaunchHostFunc");
+  checkCuda(cudaLaunchHostFunc(static_cast<cudaStream_t>(getStream()), hostFuncTrampoline, heap), "cudaLaunchHostFunc");
 }
 
 void Engine::wait()
 {
   makeCurrent();
   checkCuda(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
+  for (void* s : aux)
+    if (s) checkCuda(cudaStreamSynchronize(static_cast<cudaStream_t>(s)), "cudaStreamSynchronize");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -185,7 +185,16 @@ public:
   Engine(int deviceID, void* userStream);
   ~Engine();
   int getDeviceID() const { return deviceID; }
-  void* getStream() const { return stream; }
+  // The stream ops launch on: the engine's main stream (the user's, or its own), or -- while a staged frame is
+  // being enqueued (UNetFilter, device parameter "staging") -- the engine's internal compute stream.
+  void* getStream() const { return active ? active : stream; }
+  void* getMainStream() const { return stream; }
+  bool ownsStream() const { return ownStream; }
+  void setActiveStream(void* s) { active = s; }
+  // Internal streams of the staging pipeline (created on first use): tile copy-in, compute, tile copy-out.
+  enum AuxStream { CopyIn = 0, Compute = 1, CopyOut = 2 };
+  void* getAuxStream(AuxStream which);
+  void* newEvent();                 // cudaEvent_t without timing, owned by the engine
   void makeCurrent() const;
 
   std::shared_ptr<Conv> newConv(const ConvDesc& desc) { return std::make_shared<Conv>(this, desc); }
@@ -205,11 +214,14 @@ public:
   void submitCopy(void* dst, const void* src, size_t bytes); // async on the engine's stream
   void submitCopy2D(void* dst, size_t dstPitch, const void* src, size_t srcPitch, size_t widthBytes, size_t height);
   void submitHostFunc(std::function<void()>&& f);
-  void wait();
+  void wait();                      // main stream and the internal streams
 
 private:
   int deviceID;
   void* stream = nullptr;
+  void* active = nullptr;
+  void* aux[3] = {nullptr, nullptr, nullptr};
+  std::vector<void*> events;
   bool ownStream = false;
 };
 

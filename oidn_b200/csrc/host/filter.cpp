@@ -7,6 +7,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 
 namespace oidnb200 {
 
@@ -293,14 +294,13 @@ void UNetFilter::cleanup()
 
 void UNetFilter::dropFrameGraph()
 {
-  if (frameGraph.exec)
-  {
-    device->getEngine(0)->makeCurrent();
-    cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(frameGraph.exec));
-    frameGraph.exec = nullptr;
-  }
-  frameGraph.key.clear();
-  frameGraph.seen.clear();
+  for (FrameGraph& g : frameGraphs)
+    if (g.exec)
+    {
+      device->getEngine(0)->makeCurrent();
+      cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g.exec));
+    }
+  frameGraphs.clear();
 }
 
 // Everything a frame's kernel arguments depend on besides the committed model.
@@ -327,6 +327,7 @@ std::vector<uint64_t> UNetFilter::frameKey() const
 void UNetFilter::freeScratch()
 {
   dropFrameGraph();
+  freeStaging();
   for (size_t i = 0; i < instances.size(); ++i)
     if (instances[i].scratch)
     {
@@ -500,9 +501,10 @@ bool UNetFilter::buildModel(const TilePlan& cand, size_t maxMemoryByteSize, bool
     Instance& inst = instances.back();
     inst.graph.reset(new Graph(engine, constTensors));
     Graph& g = *inst.graph;
-    auto in = g.addInputProcess("input", TensorDesc{inputC, cand.tileH, cand.tileW}, transferFunc, hdr, snorm);
+    inst.transferFunc = newTransferFunc();
+    auto in = g.addInputProcess("input", TensorDesc{inputC, cand.tileH, cand.tileW}, inst.transferFunc, hdr, snorm);
     auto x = largeModel ? addUNetLarge(g, in) : addUNet(g, in);
-    g.addOutputProcess("output", x, transferFunc, hdr, snorm);
+    g.addOutputProcess("output", x, inst.transferFunc, hdr, snorm);
 
     const size_t graphScratch = round_up(g.getScratchByteSize(), memoryAlignment);
     size_t scratch = graphScratch;
@@ -590,41 +592,276 @@ void UNetFilter::init()
   }
 }
 
-namespace {
-struct ProgressState
+// Progress of one execute(): every op advances it by one unit (core/op.cpp:8-22, core/progress.cpp:17-39),
+// from host callbacks in stream order; engines of a multi-GPU device report concurrently.
+struct UNetFilter::ProgressState
 {
   ProgressMonitorFunction func;
   void* userPtr;
   double total;
-  std::atomic<double> done{0};
+  double done = 0;
+  std::mutex mutex;
   std::atomic<bool> cancelled{false};
   void update(double amount)
   {
+    std::lock_guard<std::mutex> lock(mutex);
     if (cancelled) return;
-    const double d = done.load() + amount;
-    done.store(d);
-    if (!func(userPtr, std::min(d / total, 1.0))) cancelled = true;
+    done += amount;
+    if (!func(userPtr, std::min(done / total, 1.0))) cancelled = true;
   }
 };
-} // namespace
 
-void UNetFilter::execute(SyncMode sync)
+// ------------------------------------------------------------------------------------------------
+// Tile staging
+// ------------------------------------------------------------------------------------------------
+static bool packedPixels(const Image& im) { return !im || im.pixelStride == formatBytes(im.format); }
+
+bool UNetFilter::wantStaging() const
 {
-  if (dirty) throw Exception(Error::InvalidOperation, "changes to the filter are not committed");
-  if (plan.H <= 0 || plan.W <= 0) return;
-  const int numEngines = device->getNumEngines();
-
-  // Progress: one unit per tile (+1 for autoexposure, +1 for the final copy), reported from
-  // host callbacks in stream order (core/progress.cpp:17-39 reports per op; per tile here).
-  std::shared_ptr<ProgressState> progress;
-  if (progressFunc)
+  const int mode = device->getInt("staging");
+  if (mode == 0 || numShards > 1) return false;  // sharded processes stage their own tiles (oidn_b200/sharded.py)
+  // copy engines move whole row segments: every image must have packed pixels
+  if (!packedPixels(color) || !packedPixels(albedo) || !packedPixels(normal) || !packedPixels(output)) return false;
+  if (mode > 0) return true;
+  // auto: the frame is not in the memory of (all of) the GPUs that run its tiles
+  const bool multi = device->getNumEngines() > 1;
+  for (const Image* im : {&color, &albedo, &normal, &output})
   {
-    progress = std::make_shared<ProgressState>();
-    progress->func = progressFunc; progress->userPtr = progressUserPtr;
-    progress->total = (double)((tiles.size() + numShards - 1 - shardIndex) / numShards) +
-                      ((hdr && std::isnan(inputScale) && !inputScaleDevPtr) ? 1 : 0) + (outputTemp ? 1 : 0);
-    if (!progressFunc(progressUserPtr, 0.)) throw Exception(Error::Cancelled, "execution was cancelled");
+    if (!*im) continue;
+    const Storage st = device->getPtrStorage(im->ptr);
+    if (st == Storage::Host || (multi && st == Storage::Device)) return true;
   }
+  return false;
+}
+
+void UNetFilter::freeStaging()
+{
+  for (size_t i = 0; i < staging.buffers.size(); ++i)
+    device->getEngine(staging.bufferEngine[i])->free(staging.buffers[i]);
+  staging = Staging(); // events belong to the engines
+}
+
+void UNetFilter::ensureStaging()
+{
+  if (staging.allocated) return;
+  const int E = device->getNumEngines();
+  const Image* ins[3] = {&color, &albedo, &normal};
+  auto pitchOf = [&](const Image& im) { return im ? round_up((size_t)plan.tileW * im.pixelStride, memoryAlignment) : (size_t)0; };
+  for (int k = 0; k < 3; ++k) staging.inPitch[k] = pitchOf(*ins[k]);
+  staging.outPitch = pitchOf(output);
+  staging.tilesOf.assign(E, {});
+  for (size_t i = 0; i < tiles.size(); ++i) staging.tilesOf[i % E].push_back((int)i);
+  auto alloc = [&](int e, size_t bytes) {
+    void* p = device->getEngine(e)->malloc(bytes);
+    staging.buffers.push_back(p); staging.bufferEngine.push_back(e);
+    return p;
+  };
+  staging.slots.assign(E, {});
+  staging.scale.assign(E, nullptr);
+  staging.evStart.assign(E, nullptr); staging.evEnd.assign(E, nullptr);
+  for (int par = 0; par < 2; ++par) staging.evBins[par].assign(E, nullptr);
+  for (int e = 0; e < E; ++e)
+  {
+    Engine* eng = device->getEngine(e);
+    staging.slots[e].resize(2 * staging.tilesOf[e].size());
+    for (Slot& sl : staging.slots[e])
+    {
+      for (int k = 0; k < 3; ++k)
+        if (*ins[k]) sl.in[k] = alloc(e, staging.inPitch[k] * plan.tileH);
+      sl.out = alloc(e, staging.outPitch * plan.tileH);
+      sl.evIn = eng->newEvent(); sl.evDone = eng->newEvent(); sl.evOut = eng->newEvent();
+    }
+    staging.scale[e] = static_cast<float*>(alloc(e, memoryAlignment));
+    staging.evStart[e] = eng->newEvent(); staging.evEnd[e] = eng->newEvent();
+    for (int par = 0; par < 2; ++par) staging.evBins[par][e] = eng->newEvent();
+  }
+  if (hdr && color)
+  {
+    int nbh = 0, nbw = 0;
+    oidnb200_autoexposure_bin_grid(color.H, color.W, &nbh, &nbw);
+    staging.numBins = nbh * nbw;
+    for (int par = 0; par < 2; ++par)
+    {
+      staging.bins[par] = static_cast<float*>(alloc(0, (size_t)staging.numBins * sizeof(float)));
+      staging.evScale[par] = device->getEngine(0)->newEvent();
+    }
+  }
+  staging.evJoin = device->getEngine(0)->newEvent();
+  staging.allocated = true;
+}
+
+// Smallest bin index i in [0, n] whose first pixel i*size/n is >= x (bins of core/autoexposure.h:20-24).
+static int firstBinAtOrAfter(int x, int n, int size)
+{
+  int i = (int)std::min<long>(n, ((long)x * n + size - 1) / size);
+  while (i > 0 && (long)(i - 1) * size / n >= x) --i;
+  while (i < n && (long)i * size / n < x) ++i;
+  return i;
+}
+
+static inline cudaStream_t cs(void* s) { return static_cast<cudaStream_t>(s); }
+static inline cudaEvent_t ce(void* e) { return static_cast<cudaEvent_t>(e); }
+
+void UNetFilter::submitFrameStaged(const std::shared_ptr<ProgressState>& progress)
+{
+  ensureStaging();
+  Staging& S = staging;
+  const int E = device->getNumEngines();
+  const int par = (int)(S.frame++ & 1);
+  const bool autoScale = hdr && color && std::isnan(inputScale) && !inputScaleDevPtr;
+  const bool profiling = device->getInt("profile") != 0;
+  const Image* ins[3] = {&color, &albedo, &normal};
+  // The copy-in is ordered after everything enqueued on the main stream(s) before this call (buffer writes, the
+  // caller's own work). The frame's join back into the main stream is deferred on streams the engines own (see
+  // the end of this function), so that order does not drag the previous frame's copy-out along.
+
+  auto report = [&](Engine* e) {
+    if (progress) { auto p = progress; e->submitHostFunc([p]() { p->update(1.); }); }
+  };
+  auto virtualImage = [](const Image& user, void* buf, size_t pitch, int h0, int w0) {
+    Image v = user; // full-frame coordinates; only the staged rectangle is ever touched
+    v.ptr = static_cast<uint8_t*>(buf) - ((size_t)h0 * pitch + (size_t)w0 * user.pixelStride);
+    v.rowStride = pitch;
+    return v;
+  };
+
+  // ---- copy-in (+ the autoexposure bins of the tiles as they land)
+  int nbh = 0, nbw = 0;
+  if (autoScale) oidnb200_autoexposure_bin_grid(color.H, color.W, &nbh, &nbw);
+  for (int e = 0; e < E; ++e)
+  {
+    Engine* eng = device->getEngine(e);
+    eng->makeCurrent();
+    cudaStream_t in = cs(eng->getAuxStream(Engine::CopyIn));
+    checkCuda(cudaEventRecord(ce(S.evStart[e]), cs(eng->getMainStream())), "cudaEventRecord");
+    checkCuda(cudaStreamWaitEvent(in, ce(S.evStart[e]), 0), "cudaStreamWaitEvent");
+    const size_t T = S.tilesOf[e].size();
+    for (size_t j = 0; j < T; ++j)
+    {
+      const TileRect& t = tiles[S.tilesOf[e][j]];
+      Slot& sl = S.slots[e][par * T + j];
+      checkCuda(cudaStreamWaitEvent(in, ce(sl.evDone), 0), "cudaStreamWaitEvent"); // frame f-2 has consumed the slot
+      for (int k = 0; k < 3; ++k)
+      {
+        const Image& im = *ins[k];
+        if (!im) continue;
+        const uint8_t* src = static_cast<const uint8_t*>(im.ptr) + (size_t)t.hSrc * im.rowStride + (size_t)t.wSrc * im.pixelStride;
+        checkCuda(cudaMemcpy2DAsync(sl.in[k], S.inPitch[k], src, im.rowStride, (size_t)t.W1 * im.pixelStride, t.H1,
+                                    cudaMemcpyDefault, in), "cudaMemcpy2DAsync (tile copy-in)");
+      }
+      if (autoScale)
+      {
+        // bins whose first pixel lies in the tile's destination rectangle: these rectangles partition the bin
+        // grid, and a bin (<= 16 px) never leaves the source rectangle (overlap >= 96 px at interior edges)
+        const int bh0 = firstBinAtOrAfter(t.hDst, nbh, color.H), bh1 = firstBinAtOrAfter(t.hDst + t.H2, nbh, color.H);
+        const int bw0 = firstBinAtOrAfter(t.wDst, nbw, color.W), bw1 = firstBinAtOrAfter(t.wDst + t.W2, nbw, color.W);
+        const Image v = virtualImage(color, sl.in[0], S.inPitch[0], t.hSrc, t.wSrc);
+        const oidnb200_image vi{v.ptr, (int)v.format, v.W, v.H, v.pixelStride, v.rowStride};
+        checkABI(oidnb200_autoexposure_bins_launch(&vi, bh0, bh1, bw0, bw1, S.bins[par], in), "autoexposure bins");
+      }
+      checkCuda(cudaEventRecord(ce(sl.evIn), in), "cudaEventRecord");
+    }
+    if (autoScale) checkCuda(cudaEventRecord(ce(S.evBins[par][e]), in), "cudaEventRecord");
+  }
+
+  // ---- input scale (core/unet_filter.cpp:172-189)
+  if (autoScale)
+  {
+    Engine* e0 = device->getEngine(0);
+    e0->makeCurrent();
+    cudaStream_t c0 = cs(e0->getAuxStream(Engine::Compute));
+    for (int e = 0; e < E; ++e) checkCuda(cudaStreamWaitEvent(c0, ce(S.evBins[par][e]), 0), "cudaStreamWaitEvent");
+    checkABI(oidnb200_autoexposure_reduce_launch(S.bins[par], S.numBins, S.scale[0] + par, c0), "autoexposure reduce");
+    for (int e = 1; e < E; ++e)
+      checkCuda(cudaMemcpyAsync(S.scale[e] + par, S.scale[0] + par, sizeof(float), cudaMemcpyDefault, c0), "cudaMemcpyAsync (input scale)");
+    checkCuda(cudaEventRecord(ce(S.evScale[par]), c0), "cudaEventRecord");
+    if (progress) { e0->setActiveStream(c0); report(e0); e0->setActiveStream(nullptr); }
+  }
+
+  // ---- the network on the staged tiles
+  for (int e = 0; e < E; ++e)
+  {
+    Engine* eng = device->getEngine(e);
+    Instance& inst = instances[e];
+    eng->makeCurrent();
+    cudaStream_t comp = cs(eng->getAuxStream(Engine::Compute));
+    if (autoScale)
+    {
+      checkCuda(cudaStreamWaitEvent(comp, ce(S.evScale[par]), 0), "cudaStreamWaitEvent");
+      inst.transferFunc->setInputScale(S.scale[e] + par);
+    }
+    else if (inputScaleDevPtr) inst.transferFunc->setInputScale(inputScaleDevPtr);
+    else inst.transferFunc->setInputScale(std::isnan(inputScale) ? 1.f : inputScale);
+    const size_t T = S.tilesOf[e].size();
+    eng->setActiveStream(comp);
+    try
+    {
+      for (size_t j = 0; j < T; ++j)
+      {
+        if (progress && progress->cancelled) break;
+        const TileRect& t = tiles[S.tilesOf[e][j]];
+        Slot& sl = S.slots[e][par * T + j];
+        checkCuda(cudaStreamWaitEvent(comp, ce(sl.evIn), 0), "cudaStreamWaitEvent");
+        checkCuda(cudaStreamWaitEvent(comp, ce(sl.evOut), 0), "cudaStreamWaitEvent"); // frame f-2's output has left the slot
+        Image vin[3];
+        for (int k = 0; k < 3; ++k)
+          if (*ins[k]) vin[k] = virtualImage(*ins[k], sl.in[k], S.inPitch[k], t.hSrc, t.wSrc);
+        inst.inputProcess->setSrc(vin[0], vin[1], vin[2]);
+        inst.outputProcess->setDst(virtualImage(output, sl.out, S.outPitch, t.hDst, t.wDst));
+        inst.graph->setProfiling(profiling);
+        inst.graph->setFuseOutput(device->getInt("fuseOutput") != 0);
+        inst.graph->setOpCallback(progress ? std::function<void()>([&, eng]() { report(eng); }) : std::function<void()>());
+        inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
+        inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
+        inst.graph->submit();
+        inst.graph->setOpCallback(std::function<void()>());
+        checkCuda(cudaEventRecord(ce(sl.evDone), comp), "cudaEventRecord");
+      }
+    }
+    catch (...) { eng->setActiveStream(nullptr); throw; }
+    eng->setActiveStream(nullptr);
+  }
+
+  // ---- copy-out; in-place filtering: no rectangle may be written before every tile of the frame has been read
+  for (int e = 0; e < E; ++e)
+  {
+    Engine* eng = device->getEngine(e);
+    eng->makeCurrent();
+    cudaStream_t out = cs(eng->getAuxStream(Engine::CopyOut));
+    const size_t T = S.tilesOf[e].size();
+    if (inplace)
+      for (int e2 = 0; e2 < E; ++e2)
+        for (size_t j2 = 0; j2 < S.tilesOf[e2].size(); ++j2)
+          checkCuda(cudaStreamWaitEvent(out, ce(S.slots[e2][par * S.tilesOf[e2].size() + j2].evIn), 0), "cudaStreamWaitEvent");
+    for (size_t j = 0; j < T; ++j)
+    {
+      const TileRect& t = tiles[S.tilesOf[e][j]];
+      Slot& sl = S.slots[e][par * T + j];
+      checkCuda(cudaStreamWaitEvent(out, ce(sl.evDone), 0), "cudaStreamWaitEvent");
+      uint8_t* dst = static_cast<uint8_t*>(output.ptr) + (size_t)t.hDst * output.rowStride + (size_t)t.wDst * output.pixelStride;
+      checkCuda(cudaMemcpy2DAsync(dst, output.rowStride, sl.out, S.outPitch, (size_t)t.W2 * output.pixelStride, t.H2,
+                                  cudaMemcpyDefault, out), "cudaMemcpy2DAsync (tile copy-out)");
+      checkCuda(cudaEventRecord(ce(sl.evOut), out), "cudaEventRecord");
+    }
+    checkCuda(cudaEventRecord(ce(S.evEnd[e]), out), "cudaEventRecord");
+  }
+
+  // ---- join: the main stream(s) continue when the whole frame is in the output image (Device::submitBarrier).
+  // A stream the caller supplied is joined now (the caller may enqueue anything behind this call). Streams the
+  // engines own are joined lazily -- before the next buffer operation, in-place frame or synchronisation
+  // (Device::joinStaged) -- so back-to-back staged frames overlap: copy-in of frame f+1 and copy-out of frame
+  // f-1 run under the convolutions of frame f.
+  device->deferJoin(S.evEnd);
+  bool userStream = false;
+  for (int e = 0; e < E; ++e) userStream |= !device->getEngine(e)->ownsStream();
+  if (userStream) device->joinStaged();
+}
+
+// The frame with every image dereferenced in place by the kernels (the reference's contract).
+void UNetFilter::submitFrame(const std::shared_ptr<ProgressState>& progress)
+{
+  const int numEngines = device->getNumEngines();
+  const bool profiling = device->getInt("profile") != 0;
   auto report = [&](Engine* e) {
     if (progress) { auto p = progress; e->submitHostFunc([p]() { p->update(1.); }); }
   };
@@ -635,88 +872,146 @@ void UNetFilter::execute(SyncMode sync)
       throw Exception(Error::Cancelled, "execution was cancelled");
     }
   };
+  auto setScale = [&](float v) { for (auto& inst : instances) inst.transferFunc->setInputScale(v); };
+  auto setScalePtr = [&](const float* p) { for (auto& inst : instances) inst.transferFunc->setInputScale(p); };
 
-  const bool profiling = device->getInt("profile") != 0;
-  auto submitFrame = [&]() {
-    // input scale (core/unet_filter.cpp:172-189)
-    if (inputScaleDevPtr)
-      transferFunc->setInputScale(inputScaleDevPtr);
-    else if (std::isnan(inputScale))
+  // input scale (core/unet_filter.cpp:172-189)
+  if (inputScaleDevPtr)
+    setScalePtr(inputScaleDevPtr);
+  else if (std::isnan(inputScale))
+  {
+    if (hdr)
     {
-      if (hdr)
-      {
-        autoexposure->setSrc(color);
-        device->getEngine(0)->makeCurrent();
-        autoexposure->submit();
-        report(device->getEngine(0));
-        device->submitBarrier();
-        transferFunc->setInputScale(autoexposure->getDstPtr());
-      }
-      else
-        transferFunc->setInputScale(1.f);
+      autoexposure->setSrc(color);
+      device->getEngine(0)->makeCurrent();
+      autoexposure->submit();
+      report(device->getEngine(0));
+      device->submitBarrier();
+      setScalePtr(autoexposure->getDstPtr());
     }
     else
-      transferFunc->setInputScale(inputScale);
+      setScale(1.f);
+  }
+  else
+    setScale(inputScale);
 
-    for (auto& inst : instances)
-    {
-      inst.inputProcess->setSrc(color, albedo, normal);
-      inst.outputProcess->setDst(outputTemp ? outputTemp : output);
-    }
+  for (auto& inst : instances)
+  {
+    inst.inputProcess->setSrc(color, albedo, normal);
+    inst.outputProcess->setDst(outputTemp ? outputTemp : output);
+  }
 
-    int tileIndex = 0, globalIndex = 0;
-    for (const TileRect& t : tiles)
-    {
-      if (globalIndex++ % numShards != shardIndex) continue; // another process's tile
-      checkCancel();
-      Instance& inst = instances[tileIndex % numEngines];
-      inst.graph->setProfiling(profiling);
-      inst.graph->setFuseOutput(device->getInt("fuseOutput") != 0);
-      inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
-      inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
-      inst.graph->submit();
-      report(device->getEngine(tileIndex % numEngines));
-      ++tileIndex;
-    }
-    device->submitBarrier();
+  int tileIndex = 0, globalIndex = 0;
+  std::vector<const TileRect*> mine;
+  for (const TileRect& t : tiles)
+  {
+    if (globalIndex++ % numShards != shardIndex) continue; // another process's tile
+    checkCancel();
+    Engine* eng = device->getEngine(tileIndex % numEngines);
+    Instance& inst = instances[tileIndex % numEngines];
+    inst.graph->setProfiling(profiling);
+    inst.graph->setFuseOutput(device->getInt("fuseOutput") != 0);
+    inst.graph->setOpCallback(progress ? std::function<void()>([&, eng]() { report(eng); }) : std::function<void()>());
+    inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
+    inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
+    inst.graph->submit();
+    inst.graph->setOpCallback(std::function<void()>());
+    mine.push_back(&t);
+    ++tileIndex;
+  }
+  device->submitBarrier();
 
-    if (outputTemp)
+  if (outputTemp)
+  {
+    // in-place filtering of a multi-tile frame went through a temporary (core/unet_filter.cpp:245-249)
+    device->getEngine(0)->makeCurrent();
+    if (numShards == 1)
     {
-      device->getEngine(0)->makeCurrent();
+      imageCopy->setSrc(outputTemp);
       imageCopy->setDst(output);
       imageCopy->submit();
-      report(device->getEngine(0));
     }
-  };
+    else
+      // a shard has written only its own tiles: copy back exactly those rectangles (the rest of the
+      // temporary is uninitialised, and the other shards' rectangles of `output` are theirs)
+      for (const TileRect* t : mine)
+      {
+        auto view = [&](const Image& im) {
+          Image v = im;
+          v.ptr = static_cast<uint8_t*>(im.ptr) + (size_t)t->hDst * im.rowStride + (size_t)t->wDst * im.pixelStride;
+          v.H = t->H2; v.W = t->W2;
+          return v;
+        };
+        imageCopy->setSrc(view(outputTemp));
+        imageCopy->setDst(view(output));
+        imageCopy->submit();
+      }
+    report(device->getEngine(0));
+  }
+}
+
+void UNetFilter::execute(SyncMode sync)
+{
+  if (dirty) throw Exception(Error::InvalidOperation, "changes to the filter are not committed");
+  if (plan.H <= 0 || plan.W <= 0) return;
+  const int numEngines = device->getNumEngines();
+  const bool staged = wantStaging();
+  lastStaged = staged;
+  const bool autoScale = hdr && std::isnan(inputScale) && !inputScaleDevPtr;
+  const bool profiling = device->getInt("profile") != 0;
+
+  // Progress: one unit per op of every tile (+1 for the autoexposure, +1 for the final copy of an in-place
+  // multi-tile frame), as core/unet_filter.cpp:155-168 counts it.
+  std::shared_ptr<ProgressState> progress;
+  if (progressFunc)
+  {
+    progress = std::make_shared<ProgressState>();
+    progress->func = progressFunc; progress->userPtr = progressUserPtr;
+    const double myTiles = (double)((tiles.size() + numShards - 1 - shardIndex) / numShards);
+    progress->total = myTiles * getNumOps() + (autoScale ? 1 : 0) + ((outputTemp && !staged) ? 1 : 0);
+    if (!progressFunc(progressUserPtr, 0.)) throw Exception(Error::Cancelled, "execution was cancelled");
+  }
 
   // Frame-stream path: replay (or capture) the frame as one CUDA graph.
-  const bool graphable = device->getInt("graph") != 0 && numEngines == 1 && !progress && !profiling;
-  if (graphable)
+  const bool graphable = device->getInt("graph") != 0 && numEngines == 1 && !progress && !profiling && !staged;
+  if (staged)
+    submitFrameStaged(progress);
+  else if (graphable)
   {
+    device->joinStaged();
     Engine* e0 = device->getEngine(0);
     cudaStream_t st = static_cast<cudaStream_t>(e0->getStream());
     const std::vector<uint64_t> key = frameKey();
     e0->makeCurrent();
-    if (frameGraph.exec && frameGraph.key == key)
-      checkCuda(cudaGraphLaunch(static_cast<cudaGraphExec_t>(frameGraph.exec), st), "cudaGraphLaunch");
-    else if (frameGraph.seen != key)
+    FrameGraph* fg = nullptr;
+    for (FrameGraph& g : frameGraphs)
+      if (g.key == key) fg = &g;
+    if (!fg)
     {
-      // first frame with these arguments: run it eagerly (also warms one-time kernel attributes)
-      frameGraph.seen = key;
-      submitFrame();
+      if (frameGraphs.size() >= maxFrameGraphs)
+      {
+        size_t lru = 0;
+        for (size_t i = 1; i < frameGraphs.size(); ++i)
+          if (frameGraphs[i].lastUse < frameGraphs[lru].lastUse) lru = i;
+        if (frameGraphs[lru].exec) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(frameGraphs[lru].exec));
+        frameGraphs.erase(frameGraphs.begin() + lru);
+      }
+      frameGraphs.emplace_back();
+      fg = &frameGraphs.back();
+      fg->key = key;
     }
+    fg->lastUse = ++frameGraphClock;
+    if (fg->exec)
+      checkCuda(cudaGraphLaunch(static_cast<cudaGraphExec_t>(fg->exec), st), "cudaGraphLaunch");
+    else if (fg->seen++ == 0)
+      submitFrame(progress); // first frame with these arguments: run it eagerly (also warms one-time kernel attributes)
     else
     {
-      if (frameGraph.exec)
-      {
-        cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(frameGraph.exec));
-        frameGraph.exec = nullptr;
-      }
       cudaGraph_t g = nullptr;
       checkCuda(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
       try
       {
-        submitFrame();
+        submitFrame(progress);
       }
       catch (...)
       {
@@ -730,13 +1025,15 @@ void UNetFilter::execute(SyncMode sync)
       const cudaError_t ie = cudaGraphInstantiate(&exec, g, 0);
       cudaGraphDestroy(g);
       checkCuda(ie, "cudaGraphInstantiate");
-      frameGraph.exec = exec;
-      frameGraph.key = key;
+      fg->exec = exec;
       checkCuda(cudaGraphLaunch(exec, st), "cudaGraphLaunch");
     }
   }
   else
-    submitFrame();
+  {
+    device->joinStaged();
+    submitFrame(progress);
+  }
 
   if (profiling)
     for (auto& inst : instances) inst.graph->collectProfile(profile);

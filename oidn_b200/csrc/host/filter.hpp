@@ -106,6 +106,7 @@ public:
   bool isLargeModel() const { return largeModel; }
   size_t getScratchByteSize() const { return totalMemoryByteSize; }
   int getNumOps() const { return instances.empty() ? 0 : instances[0].graph->getNumOps(); }
+  bool wasStaged() const { return lastStaged; }
   // per-op device times accumulated since the last reset (device param "profile" = 1)
   std::vector<Graph::OpTime> getProfile();
   void resetProfile() { profile.clear(); }
@@ -162,9 +163,52 @@ private:
     std::unique_ptr<Graph> graph;
     std::shared_ptr<InputProcess> inputProcess;
     std::shared_ptr<OutputProcess> outputProcess;
+    std::shared_ptr<TransferFunction> transferFunc; // per engine: a staged frame gives every GPU its own copy of the input scale
     void* scratch = nullptr;
     size_t scratchByteSize = 0;
   };
+
+  // Tile staging (device parameter "staging": -1 auto, 0 off, 1 on). When the frame does not live
+  // in the memory of the GPU that runs a tile -- pinned host memory, or another GPU of a multi-GPU device --
+  // the tile's source rectangles are brought into engine-local staging images by copy engines, the network
+  // runs on local data, and the output rectangle goes back by a copy engine: three internal streams per engine
+  // (copy-in, compute, copy-out) linked by events, two slot sets alternating between frames, so the copy-in of
+  // frame f+1 and the copy-out of frame f-1 overlap the convolutions of frame f (what `oidnBenchmark --buffer
+  // hostcopy` leaves to the application: apps/oidnBenchmark.cpp:165-180,343-359) and every GPU of a multi-GPU
+  // device pulls its own tiles over its own PCIe link / NVLink port. Autoexposure on a staged frame: each tile
+  // fills the bins it owns straight into engine 0's bin array (peer stores), engine 0 folds it in the fixed
+  // order and hands every engine the scale -- bit-identical to the in-place pass. No NCCL, no host thread.
+  struct Slot
+  {
+    void* in[3] = {nullptr, nullptr, nullptr};   // staged color / albedo / normal source rectangle (tile sized)
+    void* out = nullptr;                          // staged output rectangle
+    void* evIn = nullptr;                         // inputs have landed
+    void* evDone = nullptr;                       // the network has consumed the inputs and written the output
+    void* evOut = nullptr;                        // the output has left the slot
+  };
+  struct Staging
+  {
+    bool allocated = false;
+    size_t inPitch[3] = {0, 0, 0}, outPitch = 0;
+    std::vector<std::vector<int>> tilesOf;        // [engine] -> indices into `tiles`
+    std::vector<std::vector<Slot>> slots;         // [engine][parity * tilesOf[engine].size() + j]
+    std::vector<float*> scale;                    // [engine] -> 2 floats (one per parity)
+    float* bins[2] = {nullptr, nullptr};          // engine 0: autoexposure bin array per parity
+    int numBins = 0;
+    std::vector<void*> evBins[2];                 // [parity][engine]: the engine's tiles have filled their bins
+    void* evScale[2] = {nullptr, nullptr};        // engine 0 has distributed the scale
+    std::vector<void*> evStart, evEnd;            // [engine]: frame start on the main stream / all copy-outs issued
+    void* evJoin = nullptr;
+    std::vector<void*> buffers;                   // every device allocation, with its engine
+    std::vector<int> bufferEngine;
+    uint64_t frame = 0;
+  } staging;
+  bool wantStaging() const;
+  void ensureStaging();
+  void freeStaging();
+  struct ProgressState;
+  void submitFrameStaged(const std::shared_ptr<ProgressState>& progress);
+  void submitFrame(const std::shared_ptr<ProgressState>& progress);
 
   Data userWeightsBlob;
   std::shared_ptr<std::vector<uint8_t>> builtinBlob; // keeps a file-loaded model alive
@@ -176,6 +220,7 @@ private:
   std::vector<TileRect> tiles;
   TilePlan plan;
   bool largeModel = false;
+  bool lastStaged = false;
   bool inplace = false;
   int inplaceParam = 0;
   size_t totalMemoryByteSize = 0;
@@ -185,11 +230,18 @@ private:
   // is captured into a CUDA graph the second time the filter runs with the same image pointers and
   // input scale, and replayed with one cudaGraphLaunch afterwards. Pointer / stride / scale changes
   // re-capture (they are kernel arguments); commit() and scratch reallocation drop the graph.
+  // A few keys are remembered (least recently used goes first), so a caller that alternates between two or
+  // three output buffers still replays graphs instead of re-capturing (or never capturing) every frame.
   struct FrameGraph
   {
-    std::vector<uint64_t> key, seen;
+    std::vector<uint64_t> key;
+    int seen = 0;         // frames run with this key so far
     void* exec = nullptr; // cudaGraphExec_t
-  } frameGraph;
+    uint64_t lastUse = 0;
+  };
+  static constexpr size_t maxFrameGraphs = 4;
+  std::vector<FrameGraph> frameGraphs;
+  uint64_t frameGraphClock = 0;
   std::vector<uint64_t> frameKey() const;
   void dropFrameGraph();
 };

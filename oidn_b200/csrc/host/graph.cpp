@@ -201,13 +201,16 @@ void Graph::submit()
   if (!profiling)
   {
     for (auto& op : ops)
+    {
       if (!(fused && op == outputProcess)) op->submit();
+      if (opCallback) opCallback();
+    }
     return;
   }
   cudaStream_t st = static_cast<cudaStream_t>(engine->getStream());
   for (size_t i = 0; i < ops.size(); ++i)
   {
-    if (fused && ops[i] == outputProcess) continue;
+    if (fused && ops[i] == outputProcess) { if (opCallback) opCallback(); continue; }
     cudaEvent_t e0, e1;
     checkCuda(cudaEventCreate(&e0), "cudaEventCreate");
     checkCuda(cudaEventCreate(&e1), "cudaEventCreate");
@@ -215,6 +218,7 @@ void Graph::submit()
     ops[i]->submit();
     cudaEventRecord(e1, st);
     stamps.push_back(Stamp{(int)i, e0, e1});
+    if (opCallback) opCallback();
   }
 }
 

@@ -45,6 +45,9 @@ public:
   // stream and adds the elapsed times to `out` (one entry per op, in op order).
   struct OpTime { std::string name; int kind; double ms; int launches; };
   void setProfiling(bool on) { profiling = on; }
+  // Called after every op has been enqueued (also for an output process folded into the last conv), so
+  // progress advances per op as in the reference (core/op.cpp:8-22, every op has work amount 1).
+  void setOpCallback(std::function<void()> cb) { opCallback = std::move(cb); }
   // Output process folded into the last conv's epilogue when the output image allows it (default on;
   // device parameter "fuseOutput"). Decided per submit(): it depends on the image set for the frame.
   void setFuseOutput(bool on) { fuseOutput = on; }
@@ -94,6 +97,7 @@ private:
   void* scratchBase = nullptr;
   size_t scratchSize = 0;
   void* weightBuffer = nullptr;
+  std::function<void()> opCallback;
   bool profiling = false;
   struct Stamp { int op; void* e0; void* e1; };
   std::vector<Stamp> stamps;

@@ -1,4 +1,5 @@
 #include "tza.hpp"
+#include <cstdint>
 #include <cstring>
 
 namespace oidnb200 {
@@ -50,12 +51,16 @@ std::shared_ptr<TensorMap> parseTZA(const void* buffer, size_t size)
     const uint16_t nameLen = c.read<uint16_t>();
     const std::string name = c.readString(nameLen);
     const uint8_t ndims = c.read<uint8_t>();
+    // only "x" (rank 1) and "oihw" (rank 4) tensors exist; dims become ints downstream and the element
+    // count must not wrap (a crafted blob could otherwise pass the bounds check with a wrapped byte size)
+    if (ndims != 1 && ndims != 4) throw Exception(Error::InvalidOperation, "invalid tensor layout");
     size_t count = 1;
     for (int d = 0; d < ndims; ++d)
     {
       const uint32_t v = c.read<uint32_t>();
+      if (v > (uint32_t)INT32_MAX || __builtin_mul_overflow(count, (size_t)v, &count))
+        throw Exception(Error::InvalidOperation, "invalid or corrupted weights blob");
       t.dims.push_back((int)v);
-      count *= v;
     }
     t.layout = c.readString(ndims);
     if (!((ndims == 1 && t.layout == "x") || (ndims == 4 && t.layout == "oihw")))
@@ -63,7 +68,9 @@ std::shared_ptr<TensorMap> parseTZA(const void* buffer, size_t size)
     t.dtype = (char)c.read<uint8_t>();
     if (t.dtype != 'f' && t.dtype != 'h') throw Exception(Error::InvalidOperation, "invalid tensor data type");
     const uint64_t off = c.read<uint64_t>();
-    const size_t bytes = count * (t.dtype == 'h' ? 2 : 4);
+    size_t bytes = 0;
+    if (__builtin_mul_overflow(count, (size_t)(t.dtype == 'h' ? 2 : 4), &bytes))
+      throw Exception(Error::InvalidOperation, "invalid or corrupted weights blob");
     if (off > size || bytes > size - off) throw Exception(Error::InvalidOperation, "invalid or corrupted weights blob");
     t.data = c.base + off;
     (*map)[name] = t;

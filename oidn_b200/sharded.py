@@ -142,6 +142,7 @@ class ShardedFilter:
                aux=True, frame=None, stage=True, source="rank0", own_groups=True):
     assert source in ("rank0", "distributed")
     self.dist, self.torch, self.dev = dist, torch, device
+    self._check_stream()
     self.rank, self.world = dist.get_rank(), dist.get_world_size()
     self.W, self.H, self.hdr, self.source = W, H, hdr, source
     nb = W * H * 12
@@ -206,6 +207,17 @@ class ShardedFilter:
       self.upload_tiles({n: frame[n].ctypes.data for n in self.inputs})
       self.dev.sync()
 
+  def _check_stream(self):
+    """The autoexposure kernels and the NCCL collectives are issued on torch's current stream, the filter and the
+    rectangle copies on the device's engine stream: the frame is only ordered when they are the SAME stream, i.e.
+    the device was created as api.Device((gpu,), streams=[s.cuda_stream]) and is used inside torch.cuda.stream(s)."""
+    cur = self.torch.cuda.current_stream().cuda_stream
+    have = self.dev.streams[0] if getattr(self.dev, "streams", None) else None
+    if have is None or int(have) != int(cur):
+      raise ValueError("ShardedFilter: the device must be created on torch's current stream "
+                       "(api.Device((gpu,), streams=[stream.cuda_stream]) inside torch.cuda.stream(stream)); "
+                       "device stream %s, current stream %s" % (have, cur))
+
   # ---- rectangle transfers (copy engines, stream ordered) ------------------------------------------
   def _rect(self, t, src):
     return (t["hSrc"], t["wSrc"], t["H1"], t["W1"]) if src else (t["hDst"], t["wDst"], t["H2"], t["W2"])
@@ -245,6 +257,7 @@ class ShardedFilter:
     """Enqueues one frame on the device's stream of every rank. assemble=False (distributed only)
     leaves every rank's output rectangles in its local output image (the caller downloads them)."""
     torch, dist, L = self.torch, self.dist, capi.lib()
+    self._check_stream()
     st = torch.cuda.current_stream().cuda_stream
     if self.source == "distributed":
       if self.hdr:

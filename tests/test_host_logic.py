@@ -151,6 +151,22 @@ def test_tza_parser_rejects_malformed_blobs():
   assert parse(bytes(bad))[0] == -3                           # tensor data runs past the blob
 
 
+def test_tza_parser_rejects_wrapping_dimensions():
+  """A crafted table entry whose element count wraps size_t (65536^4 = 2^64) or whose dims exceed INT_MAX must not
+  pass the bounds check with a wrapped byte size; ranks other than 1 / 4 are refused before the dims are read."""
+  def blob_with(dims, layout, dtype=b"h"):
+    name = b"enc_conv0.weight"
+    entry = struct.pack("<H", len(name)) + name + struct.pack("<B", len(dims)) + b"".join(struct.pack("<I", d) for d in dims)
+    entry += layout + dtype + struct.pack("<Q", 12)
+    return struct.pack("<HBBQ", 0x41D7, 2, 0, 12) + struct.pack("<I", 1) + entry
+  assert parse(blob_with([1, 1, 1, 1], b"oihw")) == (1, "")        # sanity: a well-formed one-element tensor parses
+  assert parse(blob_with([65536] * 4, b"oihw")) == (-3, "invalid or corrupted weights blob")
+  assert parse(blob_with([2**31, 2**31, 2, 2], b"oihw")) == (-3, "invalid or corrupted weights blob")
+  assert parse(blob_with([2**31 - 1, 2**31 - 1, 2**31 - 1, 8], b"oihw", b"f")) == (-3, "invalid or corrupted weights blob")
+  assert parse(blob_with([4, 4], b"xy")) == (-3, "invalid tensor layout")
+  assert parse(blob_with([1] * 255, b"x" * 255)) == (-3, "invalid tensor layout")
+
+
 def plan_arena(sizes, first, last):
   n = len(sizes)
   off = (C.c_size_t * n)()
