@@ -292,7 +292,11 @@ def test_shared_buffer_from_fd_round_trip():
   with pytest.raises(api.Error) as ei:
     dev.import_fd(r, 4096)                                       # not a memory object
   assert ei.value.code == capi.ERROR_INVALID_ARGUMENT
-  os.close(r); os.close(w)
+  for fd in (r, w):
+    try:
+      os.close(fd)      # the driver may already have closed the read end while probing it
+    except OSError:
+      pass
   owner = dev.new_exportable_buffer(color.nbytes)                # the "renderer" side
   with pytest.raises(api.Error):
     dev.new_buffer(64).fd()                                      # plain buffers are not exportable
