@@ -94,6 +94,11 @@ OIDNB200_API int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv
  * role, the cycles spent blocked at each barrier (tools/probe_conv --trace). No effect otherwise. */
 OIDNB200_API int oidnb200_conv_set_trace(oidnb200_conv* conv, void* trace_counters);
 
+/* In-frame timing: `stamps` = device array of 2 x uint64 {UINT64_MAX, 0} (or NULL to switch off). Every launch
+ * then records min(start) / max(end) over its CTAs in %globaltimer nanoseconds -- when the grid really ran inside
+ * a frame whose launches overlap (programmatic dependent launch), which CUDA events around a launch cannot show. */
+OIDNB200_API int oidnb200_conv_set_stamps(oidnb200_conv* conv, void* stamps);
+
 /* ------------------------------------------------------------------------------------------
  * Images, tiles, transfer functions  -- core/image.h:14-120, core/tile.h, core/color.h:10-166
  * ------------------------------------------------------------------------------------------ */

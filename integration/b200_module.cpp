@@ -13,9 +13,17 @@
 // Built with -DOIDN_B200_OP_LEVEL the same file gives INTEGRATION.md's op-level route instead: NO core change at
 // all; the reference's own filters, core/graph.cpp, arena planner and tile loop stay in charge and this module
 // only supplies the Engine's ops (Conv incl. fused Pool and the paired ConcatConv, Pool, Upsample, InputProcess,
-// OutputProcess, Autoexposure, ImageCopy) on the kernel-level C ABI (include/oidn_b200_kernels.h). First version:
-// upsampled tensors are materialised (core splits PostOp::Upsample into an Upsample op) and the output process is a
-// pass of its own; the two kernels that ConcatConvHWC asks for are recognised and run as ONE concat-conv.
+// OutputProcess, Autoexposure, ImageCopy) on the kernel-level C ABI (include/oidn_b200_kernels.h). The fusions of
+// the filter-level route are kept under the core's graph by linking ops through the tensors they share:
+//   * the two kernels that ConcatConvHWC asks for (core/concat_conv_hwc.cpp:27-31,62-80) are recognised and run as
+//     ONE concat-conv with two K segments;
+//   * PostOp::Upsample is accepted (isConvSupported), the producer stores its result at its own resolution at the
+//     start of the (4x larger) tensor the core allocated and marks the tensor; a consumer that finds its source
+//     marked reads it through the stride-0 "dup" TMA axis (virtual nearest upsample: no upsampled tensor in HBM);
+//   * the OutputProcess op finds the conv that produces its source tensor and, when the frame's output image is
+//     packed fp32 RGB, hands it its tile / image / transfer function at submit time: the conv's epilogue writes
+//     the image (oidnb200_conv_set_output_process) and the op's own kernel is skipped (core/unet_filter.cpp:228-236
+//     sets the tile before Graph::submit runs the ops in order, so the conv sees the current tile).
 //
 // Only interfaces are taken from the reference headers; no reference code is copied.
 #include "core/context.h"
@@ -98,8 +106,8 @@ OIDN_NAMESPACE_BEGIN
     cudaStream_t getStream() const { return stream; }
 
   #if defined(OIDN_B200_OP_LEVEL)
-    // Pool is fused into the conv's epilogue; PostOp::Upsample is split off by core/graph.cpp:67-80 (first version)
-    bool isConvSupported(PostOp postOp) override { return postOp == PostOp::Pool; }
+    // Pool is fused into the conv's epilogue, Upsample into the consumer's loader (see the file comment)
+    bool isConvSupported(PostOp postOp) override { return postOp == PostOp::Pool || postOp == PostOp::Upsample; }
     Ref<Conv> newConv(const ConvDesc& desc) override;
     Ref<Pool> newPool(const PoolDesc& desc) override;
     Ref<Upsample> newUpsample(const UpsampleDesc& desc) override;
@@ -112,6 +120,8 @@ OIDN_NAMESPACE_BEGIN
     // (core/concat_conv_hwc.cpp:27-31,62-67): conv1 registers under its dst tensor, conv2 finds it by its bias
     // tensor and the pair runs as one kernel with two K segments.
     std::unordered_map<const Tensor*, class B200Conv*> convByDst;
+    std::unordered_map<const Tensor*, class B200Conv*> producerOf;   // every conv, by its destination tensor
+    std::unordered_map<const Tensor*, int> halfRes;                  // tensors stored at half resolution (virtual upsample)
   #else
     Ref<Conv> newConv(const ConvDesc&) override { unsupported(); return nullptr; }
     Ref<Pool> newPool(const PoolDesc&) override { unsupported(); return nullptr; }
@@ -492,6 +502,8 @@ OIDN_NAMESPACE_BEGIN
     }
   }
 
+  class B200OutputProcess;
+
   class B200Conv final : public Conv
   {
   public:
@@ -501,16 +513,24 @@ OIDN_NAMESPACE_BEGIN
     {
       if (srcDesc.layout != TensorLayout::hwc || srcDesc.dataType != DataType::Float16 ||
           weightDesc.layout != TensorLayout::ohwi || weightDesc.dataType != DataType::Float16 ||
-          weightDesc.getH() != 3 || weightDesc.getW() != 3 || postOp == PostOp::Upsample)
+          weightDesc.getH() != 3 || weightDesc.getW() != 3)
         throw std::invalid_argument("unsupported convolution");
       accumulate = biasDesc.getRank() == 3; // second half of a ConcatConvHWC: bias = dst, dst += conv
     }
 
     ~B200Conv()
     {
-      if (dst)
-        engine->convByDst.erase(dst.get());
+      unregister();
       release();
+      detachOutputProcess();
+    }
+
+    // set by the OutputProcess that consumes this conv's tensor (B200OutputProcess::finalize)
+    B200OutputProcess* outputProcess = nullptr;
+    void detachOutputProcess();
+    bool canFuseOutput() const
+    {
+      return postOp == PostOp::None && !accumulate && weightDesc.getPaddedO() == 16 && activation == Activation::ReLU;
     }
 
     Engine* getEngine() const override { return engine; }
@@ -521,6 +541,12 @@ OIDN_NAMESPACE_BEGIN
         throw std::logic_error("convolution source/weight/bias/destination not set");
       absorbed = false;
       partner = nullptr;
+      unregister();
+      registeredDst = dst.get();
+      engine->producerOf[registeredDst] = this;
+      if (postOp == PostOp::Upsample)
+        engine->halfRes[registeredDst] = 1;
+      srcHalfRes = engine->halfRes.count(src.get()) != 0;
       if (accumulate)
       {
         auto it = engine->convByDst.find(bias.get());
@@ -534,18 +560,27 @@ OIDN_NAMESPACE_BEGIN
       prepared = false;
     }
 
-    void submitKernels(const Ref<CancellationToken>&) override
-    {
-      if (absorbed)
-        return;
-      prepare();
-      bind();
-      checkKernel(oidnb200_conv_launch(handle, engine->getStream()), "conv");
-    }
+    void submitKernels(const Ref<CancellationToken>&) override;
 
   private:
     void updateWeight() override { prepared = false; }
     void updateBias() override { prepared = false; }
+
+    void unregister()
+    {
+      if (!registeredDst)
+        return;
+      auto erase = [&](std::unordered_map<const Tensor*, B200Conv*>& m) {
+        auto it = m.find(registeredDst);
+        if (it != m.end() && it->second == this)
+          m.erase(it);
+      };
+      erase(engine->convByDst);
+      erase(engine->producerOf);
+      if (postOp == PostOp::Upsample)
+        engine->halfRes.erase(registeredDst);
+      registeredDst = nullptr;
+    }
 
     void release()
     {
@@ -579,8 +614,10 @@ OIDN_NAMESPACE_BEGIN
       d.C2 = partner ? srcDesc.getPaddedC() : 0;
       d.Cout = weightDesc.getPaddedO();
       d.relu = activation == Activation::ReLU;
-      d.post_op = postOp == PostOp::Pool ? 1 : 0;
-      d.src1_upsampled = 0;
+      d.post_op = postOp == PostOp::Pool ? 1 : 0;  // Upsample: stored at the conv's own resolution, consumers dup it
+      d.src1_upsampled = first->srcHalfRes ? 1 : 0;
+      if (partner && srcHalfRes)
+        throw std::logic_error("the second source of a concat-conv cannot be an upsampled tensor");
       d.shift_mode = 0;
       checkKernel(oidnb200_conv_create(&d, &handle), "conv create");
 
@@ -616,6 +653,8 @@ OIDN_NAMESPACE_BEGIN
     }
 
     B200Engine* engine;
+    const Tensor* registeredDst = nullptr;
+    bool srcHalfRes = false;   // the source tensor holds a half-resolution image (its producer had PostOp::Upsample)
     bool accumulate = false;
     bool absorbed = false;
     B200Conv* partner = nullptr;
@@ -689,9 +728,58 @@ OIDN_NAMESPACE_BEGIN
   {
   public:
     B200OutputProcess(B200Engine* engine, const OutputProcessDesc& desc) : OutputProcess(desc), engine(engine) {}
+    ~B200OutputProcess()
+    {
+      if (producer)
+        producer->outputProcess = nullptr;
+    }
     Engine* getEngine() const override { return engine; }
+
+    void finalize() override
+    {
+      if (producer)
+        producer->outputProcess = nullptr;
+      producer = nullptr;
+      auto it = src ? engine->producerOf.find(src.get()) : engine->producerOf.end();
+      if (it != engine->producerOf.end() && it->second->canFuseOutput())
+      {
+        producer = it->second;
+        producer->outputProcess = this;
+      }
+    }
+
+    // Called by the producing conv right before its launch: folds this op (current tile, image, transfer function)
+    // into the conv's epilogue when the kernel supports the image. Returns false -> the conv stores its tensor and
+    // this op runs as a pass of its own.
+    bool fuseInto(oidnb200_conv* conv)
+    {
+      fusedThisSubmit = false;
+      if (src && dst)
+      {
+        check();
+        const oidnb200_image d = toABI(dst);
+        const oidnb200_tile t = toABI(tile);
+        const oidnb200_transfer tf = toABI(*transferFunc);
+        const int rc = oidnb200_conv_set_output_process(conv, &t, &tf, hdr, snorm, &d);
+        if (rc == 0)
+          fusedThisSubmit = true;
+        else if (rc != OIDNB200_ERR_UNSUPPORTED)
+          checkKernel(rc, "fused output process");
+      }
+      if (!fusedThisSubmit)
+        oidnb200_conv_set_output_process(conv, nullptr, nullptr, 0, 0, nullptr);
+      return fusedThisSubmit;
+    }
+
+    void producerGone() { producer = nullptr; }
+
     void submitKernels(const Ref<CancellationToken>&) override
     {
+      if (fusedThisSubmit)
+      {
+        fusedThisSubmit = false; // the conv's epilogue has written this tile
+        return;
+      }
       check();
       const oidnb200_image d = toABI(dst);
       const oidnb200_tile t = toABI(tile);
@@ -701,7 +789,27 @@ OIDN_NAMESPACE_BEGIN
     }
   private:
     B200Engine* engine;
+    B200Conv* producer = nullptr;
+    bool fusedThisSubmit = false;
   };
+
+  void B200Conv::detachOutputProcess()
+  {
+    if (outputProcess)
+      outputProcess->producerGone();
+    outputProcess = nullptr;
+  }
+
+  void B200Conv::submitKernels(const Ref<CancellationToken>&)
+  {
+    if (absorbed)
+      return;
+    prepare();
+    bind();
+    if (outputProcess)
+      outputProcess->fuseInto(handle);
+    checkKernel(oidnb200_conv_launch(handle, engine->getStream()), "conv");
+  }
 
   class B200Autoexposure final : public Autoexposure
   {

@@ -709,7 +709,7 @@ void UNetFilter::submitFrameStaged(const std::shared_ptr<ProgressState>& progres
   const int E = device->getNumEngines();
   const int par = (int)(S.frame++ & 1);
   const bool autoScale = hdr && color && std::isnan(inputScale) && !inputScaleDevPtr;
-  const bool profiling = device->getInt("profile") != 0;
+  const int profiling = device->getInt("profile");
   const Image* ins[3] = {&color, &albedo, &normal};
   // The copy-in is ordered after everything enqueued on the main stream(s) before this call (buffer writes, the
   // caller's own work). The frame's join back into the main stream is deferred on streams the engines own (see
@@ -861,7 +861,7 @@ void UNetFilter::submitFrameStaged(const std::shared_ptr<ProgressState>& progres
 void UNetFilter::submitFrame(const std::shared_ptr<ProgressState>& progress)
 {
   const int numEngines = device->getNumEngines();
-  const bool profiling = device->getInt("profile") != 0;
+  const int profiling = device->getInt("profile");
   auto report = [&](Engine* e) {
     if (progress) { auto p = progress; e->submitHostFunc([p]() { p->update(1.); }); }
   };
@@ -958,7 +958,7 @@ void UNetFilter::execute(SyncMode sync)
   const bool staged = wantStaging();
   lastStaged = staged;
   const bool autoScale = hdr && std::isnan(inputScale) && !inputScaleDevPtr;
-  const bool profiling = device->getInt("profile") != 0;
+  const int profiling = device->getInt("profile");
 
   // Progress: one unit per op of every tile (+1 for the autoexposure, +1 for the final copy of an in-place
   // multi-tile frame), as core/unet_filter.cpp:155-168 counts it.

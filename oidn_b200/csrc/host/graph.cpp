@@ -1,6 +1,7 @@
 #include "graph.hpp"
 #include "../kernels/common.h"
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstring>
 
 namespace oidnb200 {
@@ -21,6 +22,7 @@ void Graph::clear()
   stamps.clear();
   privateByteSize = 0;
   if (weightBuffer) { engine->free(weightBuffer); weightBuffer = nullptr; }
+  if (stampBuf) { engine->free(stampBuf); stampBuf = nullptr; }
 }
 
 const ConstTensor& Graph::findConst(const std::string& name) const
@@ -198,13 +200,31 @@ void Graph::submit()
   // The output process runs inside the last conv's epilogue when the kernel supports the frame's
   // output image; otherwise (or with fuseOutput off) it is the separate pass of the reference.
   const bool fused = outputProcess && outputConv && outputProcess->fuseInto(*outputConv, fuseOutput);
-  if (!profiling)
+  if (profiling == 2 || stampBuf)
+  {
+    // in-frame stamps on (mode 2) or to be switched off again
+    const size_t n = convs.size() * 2;
+    if (profiling == 2)
+    {
+      if (!stampBuf) stampBuf = engine->malloc(n * sizeof(unsigned long long));
+      stampHost.assign(n, 0ull);
+      for (size_t i = 0; i < convs.size(); ++i) stampHost[2 * i] = ~0ull;
+      checkCuda(cudaMemcpyAsync(stampBuf, stampHost.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                                static_cast<cudaStream_t>(engine->getStream())), "cudaMemcpyAsync (stamps)");
+    }
+    for (size_t i = 0; i < convs.size(); ++i)
+      oidnb200_conv_set_stamps(convs[i].conv->getHandle(),
+                               profiling == 2 ? static_cast<unsigned long long*>(stampBuf) + 2 * i : nullptr);
+    if (profiling != 2) { engine->wait(); engine->free(stampBuf); stampBuf = nullptr; }
+  }
+  if (profiling != 1)
   {
     for (auto& op : ops)
     {
       if (!(fused && op == outputProcess)) op->submit();
       if (opCallback) opCallback();
     }
+    if (profiling == 2) collectStamps();
     return;
   }
   cudaStream_t st = static_cast<cudaStream_t>(engine->getStream());
@@ -222,9 +242,58 @@ void Graph::submit()
   }
 }
 
+void Graph::collectStamps()
+{
+  engine->wait();
+  const size_t n = convs.size();
+  checkCuda(cudaMemcpy(stampHost.data(), stampBuf, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "cudaMemcpy (stamps)");
+  stampMs.resize(n + 1, 0.); stampLaunches.resize(n + 1, 0);
+  std::vector<std::pair<unsigned long long, unsigned long long>> iv;
+  for (size_t i = 0; i < n; ++i)
+  {
+    const unsigned long long t0 = stampHost[2 * i], t1 = stampHost[2 * i + 1];
+    if (t1 <= t0) continue; // not launched
+    stampMs[i] += (double)(t1 - t0) * 1e-6;
+    stampLaunches[i] += 1;
+    iv.emplace_back(t0, t1);
+  }
+  std::sort(iv.begin(), iv.end());
+  unsigned long long total = 0, curEnd = 0;
+  for (const auto& v : iv)
+  {
+    if (v.first >= curEnd) { total += v.second - v.first; curEnd = v.second; }
+    else if (v.second > curEnd) { total += v.second - curEnd; curEnd = v.second; }
+  }
+  stampMs[n] += (double)total * 1e-6;
+  stampLaunches[n] += 1;
+}
+
 void Graph::collectProfile(std::vector<OpTime>& out)
 {
   engine->wait();
+  if (!stampMs.empty())
+  {
+    // in-frame stamp mode: one entry per op (convs filled) + the union entry
+    if (out.size() != ops.size() + 1)
+    {
+      out.clear();
+      for (auto& op : ops)
+      {
+        int kind = 0;
+        if (dynamic_cast<InputProcess*>(op.get())) kind = 1;
+        else if (dynamic_cast<OutputProcess*>(op.get())) kind = 2;
+        out.push_back(OpTime{op->getName(), kind, 0., 0});
+      }
+      out.push_back(OpTime{"conv_union", 3, 0., 0});
+    }
+    for (size_t i = 0; i < convs.size(); ++i)
+      for (size_t o = 0; o < ops.size(); ++o)
+        if (ops[o] == convs[i].conv) { out[o].ms += stampMs[i]; out[o].launches += stampLaunches[i]; }
+    out.back().ms += stampMs[convs.size()];
+    out.back().launches += stampLaunches[convs.size()];
+    stampMs.clear(); stampLaunches.clear();
+    return;
+  }
   if (out.size() < ops.size())
   {
     out.clear();

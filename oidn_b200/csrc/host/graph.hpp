@@ -44,7 +44,11 @@ public:
   // a run-time switch): submit() brackets every op with CUDA events; collectProfile() waits for the
   // stream and adds the elapsed times to `out` (one entry per op, in op order).
   struct OpTime { std::string name; int kind; double ms; int launches; };
-  void setProfiling(bool on) { profiling = on; }
+  void setProfiling(int mode) { profiling = mode; }
+  // mode 2: no events; every conv records when its grid really ran inside the frame (%globaltimer stamps written by
+  // the kernel: launches of a frame overlap through programmatic dependent launch, which events around an op
+  // serialise away). submit() then waits for the stream and accumulates per conv its interval, plus -- in an extra
+  // entry "conv_union" (kind 3) -- the length of the union of all conv intervals: the time the frame spends in convs.
   // Called after every op has been enqueued (also for an output process folded into the last conv), so
   // progress advances per op as in the reference (core/op.cpp:8-22, every op has work amount 1).
   void setOpCallback(std::function<void()> cb) { opCallback = std::move(cb); }
@@ -98,9 +102,14 @@ private:
   size_t scratchSize = 0;
   void* weightBuffer = nullptr;
   std::function<void()> opCallback;
-  bool profiling = false;
+  int profiling = 0;
   struct Stamp { int op; void* e0; void* e1; };
   std::vector<Stamp> stamps;
+  void* stampBuf = nullptr;                       // device: 2 x uint64 per conv
+  std::vector<unsigned long long> stampHost;      // init pattern / read-back
+  std::vector<double> stampMs;                    // per conv (accumulated), last entry: union
+  std::vector<int> stampLaunches;
+  void collectStamps();
 };
 
 } // namespace oidnb200

@@ -680,6 +680,13 @@ int oidnb200_conv_set_trace(oidnb200_conv* conv, void* trace_counters)
   return 0;
 }
 
+int oidnb200_conv_set_stamps(oidnb200_conv* conv, void* stamps)
+{
+  conv->plan.kp.stamps = static_cast<unsigned long long*>(stamps);
+  if (conv->fused_plan) conv->fused_plan->kp.stamps = static_cast<unsigned long long*>(stamps);
+  return 0;
+}
+
 int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv_info* info)
 {
   const ConvPlan& pl = conv->plan;

@@ -94,6 +94,13 @@ __device__ __forceinline__ Item get_item(const ConvKernelParams& p, int item)
   return it;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b)
 {
   __half2 h = __floats2half2_rn(a, b);
@@ -530,6 +537,7 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();   // this CTA's resources are the gate for the next grid's CTAs anyway
+  if (p.stamps && threadIdx.x == 0) atomicMin(&p.stamps[0], globaltimer_ns());
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + SmemLayout::tmem_ptr);
 
   // Both single-issuer roles keep warp-uniform control flow (all 32 lanes walk the loops, one
@@ -763,6 +771,7 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
   TRACE_FLUSH();
   tc_fence_before();
   __syncthreads();
+  if (p.stamps && threadIdx.x == 0) atomicMax(&p.stamps[1], globaltimer_ns());
   if (warp == 1)
   {
     tc_fence_after();

@@ -307,6 +307,54 @@ class ShardedFilter:
     self.pg_exchange = self.pg_join = None
 
 
+def single_process_device(args, torch, world, tza, host, K, Wm):
+  """bench.py's one-process arm (called on rank 0 only): api.Device((0, .., N-1)), one filter, K frames."""
+  import time
+  W, H = args.width, args.height
+  nb = W * H * 12
+  res = {}
+  # (a) the frame lives in GPU 0's HBM (single-pointer contract): every engine stages its tiles over NVLink.
+  #     Engines run on caller-supplied streams here, so each frame joins the main stream before the next starts:
+  #     device time per frame from CUDA events on engine 0's stream.
+  streams = []
+  for g in range(world):
+    with torch.cuda.device(g):
+      streams.append(torch.cuda.Stream())
+  dev = api.Device(tuple(range(world)), streams=[s.cuda_stream for s in streams]).commit()
+  with torch.cuda.device(0):
+    t = {k: torch.from_numpy(host.images[k]).cuda() for k in ("color", "albedo", "normal")}
+    out = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+  f = dev.new_filter("RT")
+  for k, v in t.items():
+    f.set_image(k, v)
+  f.set_image("output", out)
+  f.set("hdr", True); f.set("quality", api.QUALITY_HIGH); f.set_data("weights", tza)
+  f.commit()
+  info = f.info()
+  for _ in range(Wm):
+    f.execute_async()
+  dev.sync()
+  with torch.cuda.device(0):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(streams[0])
+    for _ in range(K):
+      f.execute_async()
+    e1.record(streams[0])
+  dev.sync()
+  ms = e0.elapsed_time(e1) / K
+  res["frame_in_gpu0_hbm"] = {"ms_per_step": round(ms, 4), "value": round(W * H / ms / 1e3, 1), "unit": "Mpix/s", "staged": info["staged"],
+                              "tiles": "%dx%d of %dx%d" % (info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"]),
+                              "how": "frames one after another (each joins the caller's stream): NVLink stage-in + network + stage-out "
+                                     "per frame, CUDA events on engine 0's stream"}
+  f.release(); dev.release()
+  del t, out
+  # (b) end to end: the frame lives in pinned host memory; engines on their own streams, frames pipeline in the library
+  import bench as B
+  imgs = {k: host.images[k] for k in ("color", "albedo", "normal")}
+  res["e2e_host_frame"] = B.bench_e2e_staged(api, torch, 0, imgs, tza, W, H, K, Wm, gpus=tuple(range(world)))
+  return res
+
+
 def bench_main(args, rank, world, local_rank):
   """bench.py's N>1 arm (launched by torchrun, one rank per GPU)."""
   import json
@@ -339,16 +387,46 @@ def bench_main(args, rank, world, local_rank):
   # Two frames in flight (a renderer double-buffers its frame): two device/stream/filter sets, frames
   # alternate between them, so the exchange and the copies of frame f+1 overlap the convolutions of
   # frame f. Collectives are issued in frame order by every rank.
-  def make_sets(source):
+  def make_sets(source, weights_blob=None, clean_aux=False, policy=None):
     sets = []
     for _ in range(2):
       stream = torch.cuda.Stream()
       with torch.cuda.stream(stream):
         dev = api.Device((local_rank,), streams=[stream.cuda_stream]).commit()
-        sf = ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, source=source,
+        if policy is not None:
+          dev.set("tilePolicy", policy)
+        sf = ShardedFilter(dist, torch, dev, W, H, weights_blob or tza, hdr=True, source=source, clean_aux=clean_aux,
                            frame=frame if (source == "distributed" or rank == 0) else None)
       sets.append((stream, dev, sf))
     return sets
+
+  def release_sets(sets):
+    for _, dev, sf in sets:
+      sf.release(); dev.release()
+
+  def tiles_text(sets):
+    i = sets[0][2].filter.info()
+    return "%dx%d of %dx%d, %d per rank" % (i["tileCountW"], i["tileCountH"], i["tileW"], i["tileH"],
+                                            i["tileCountH"] * i["tileCountW"] // world)
+
+  def conv_profile(sets, kind, frames=3):
+    """rank 0's convs inside its frames: union of the conv grids' in-frame intervals (device parameter profile=2)."""
+    stream, dev, sf = sets[0]
+    with torch.cuda.stream(stream):
+      dev.set("profile", 2)
+      sf.execute_async(); torch.cuda.synchronize(); sf.filter.profile()
+      for _ in range(frames):
+        sf.execute_async()
+        torch.cuda.synchronize()
+      prof = sf.filter.profile()
+      dev.set("profile", 0)
+    dist.barrier()
+    union = sum(m for _, k, _, m in prof if k == 3) / frames
+    launches = sum(n for _, k, n, _ in prof if k == 0) // frames
+    _, mine = tiles_of_rank(H, W, kind == "large", world, 0, sets[0][1].get("maxTilePixels"), sets[0][1].get("tilePolicy"))
+    my_px = sum(t["H2"] * t["W2"] for t in mine)
+    tf = weights.flops_per_pixel(kind, 9) * my_px / (union * 1e-3) / 1e12
+    return union, launches, my_px, tf
 
   def timed(sets, frame_fn, wall=False):
     """K frames alternating between the two sets; device time (events) or wall clock, max over ranks."""
@@ -380,23 +458,24 @@ def bench_main(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
       sf.execute_async()
 
+  # the tile plan: fewest recomputed pixels (tilePolicy 1) against fewest 128-pixel conv strips (tilePolicy 2); the
+  # headline is the device default, the other one is reported next to it
+  default_policy = api.Device((local_rank,)).get("tilePolicy")
+  other_policy = 2 if default_policy == 1 else 1
+  plan_alt = None
+  if not args.no_rank0:
+    alt = make_sets("distributed", policy=other_policy)
+    ms_alt, _, _ = timed(alt, run_frame)
+    plan_alt = {"tilePolicy": other_policy, "tiles": tiles_text(alt), "ms_per_step": round(ms_alt, 4),
+                "value": round(W * H / ms_alt / 1e3, 1), "unit": "Mpix/s"}
+    release_sets(alt)
+
   sets = make_sets("distributed")
   info = sets[0][2].filter.info()
   ntiles = info["tileCountH"] * info["tileCountW"]
   ms, t0, t1 = timed(sets, run_frame)
   clocks = sampler.window(t0, t1) if rank == 0 else None
-
-  # per-op times on this rank's tiles (roofline of the dominant kernel, rank 0's share): one set alone
-  stream, dev, sf = sets[0]
-  with torch.cuda.stream(stream):
-    dev.set("profile", 1)
-    sf.execute_async(); torch.cuda.synchronize(); sf.filter.profile()
-    for _ in range(K):
-      sf.execute_async()
-    torch.cuda.synchronize()
-    prof = sf.filter.profile()
-    dev.set("profile", 0)
-  dist.barrier()
+  conv_ms, conv_launches, my_px, conv_tf = conv_profile(sets, "base", frames=max(K // 4, 3))
 
   # end to end: the frame is in (shared, pinned) host memory and the result returns there; every rank
   # moves the rectangles of its own tiles over its own PCIe link
@@ -424,8 +503,8 @@ def bench_main(args, rank, world, local_rank):
            "how": "every rank: 2D copies of its tiles' source rectangles (with overlap) from the pinned host frame, sharded "
                   "execute (autoexposure bins all-reduce), 2D copies of its output rectangles into the host output frame; "
                   "all ranks' bytes summed; two frame sets alternating; wall clock, max over ranks"}
-  for _, dev, sf in sets:
-    sf.release(); dev.release()
+  nbins = sets[0][2].nbins
+  release_sets(sets)
 
   # the frame held by rank 0 alone (single-pointer contract): reported next to the headline
   on_rank0 = None
@@ -434,21 +513,44 @@ def bench_main(args, rank, world, local_rank):
     ms0, _, _ = timed(sets0, run_frame)
     on_rank0 = {"value": round(W * H / ms0 / 1e3, 1), "unit": "Mpix/s", "ms_per_step": round(ms0, 4),
                 "how": "whole frame in rank 0's HBM; peers pull tile rectangles / push output rectangles with copy engines over NVLink"}
-    for _, dev, sf in sets0:
-      sf.release(); dev.release()
+    release_sets(sets0)
+
+  # BASELINE config 3: the large UNet (cleanAux=true + quality=high: core/unet_filter.cpp:417-436,449-452) on the
+  # same 7680x4320 frame, tile-sharded the same way
+  large = None
+  if not args.no_8k:
+    tza_large = weights.model_tza("large", 9, seed=0)
+    setsL = make_sets("distributed", weights_blob=tza_large, clean_aux=True)
+    assert setsL[0][2].filter.info()["largeModel"] == 1
+    msL, _, _ = timed(setsL, run_frame)
+    cL, nL, _, tfL = conv_profile(setsL, "large")
+    large = {"workload": "RT hdr+calb+cnrm 7680x4320 quality=high (large UNet, 19 convs), tile-sharded across %d ranks" % world,
+             "ms_per_step": round(msL, 4), "value": round(W * H / msL / 1e3, 1), "unit": "Mpix/s", "tiles": tiles_text(setsL),
+             "rank0_conv_ms_per_frame": round(cL, 4), "rank0_conv_launches": nL, "rank0_conv_tflops": round(tfL, 1),
+             "rank0_conv_frac_of_burst_peak": round(tfL / peaks["bf16_tflops"], 4)}
+    release_sets(setsL)
+
+  # ONE process, ONE device object over all the GPUs: oidnb200NewCUDADevice(ids, streams, N) -- the reference's own
+  # multi-pair signature (include/OpenImageDenoise/oidn.h:150-153). No torch.distributed / NCCL on this path: the
+  # library stages every engine's tiles over NVLink (frame in GPU 0's HBM) or over each GPU's PCIe link (frame in
+  # pinned host memory) and exchanges the autoexposure bins through peer stores. The other ranks idle at a barrier.
+  single = None
+  dist.barrier()
+  if rank == 0 and not args.no_single_process:
+    try:
+      single = single_process_device(args, torch, world, tza, host, K, max(Wm, 2))
+    except Exception as e:  # noqa: BLE001
+      single = {"error": str(e)[:300]}
+  dist.barrier()
 
   if rank == 0:
     sampler.stop()
-    conv_ms = sum(m for _, kind, _, m in prof if kind == 0) / K
-    conv_launches = sum(n for _, kind, n, _ in prof if kind == 0) // K
-    # rank 0's tiles: algorithmic FLOPs of the pixels it outputs
-    _, mine = tiles_of_rank(H, W, False, world, 0)
-    my_px = sum(t["H2"] * t["W2"] for t in mine)
-    conv_tf = weights.flops_per_pixel("base", 9) * my_px / (conv_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel on rank 0 (%d launches/frame)" % conv_launches,
-                "achieved": round(conv_tf, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4), "traffic": None,
-                "peak_source": peaks_src + ", sustained dense bf16", "conv_ms_per_frame": round(conv_ms, 4),
+                "achieved": round(conv_tf, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": round(conv_tf / peaks["bf16_tflops"], 4), "traffic": None,
+                "peak_source": peaks_src + ", burst dense bf16 (the timed region is %.0f ms)" % (ms * K),
+                "conv_ms_per_frame": round(conv_ms, 4), "share_of_step": round(min(conv_ms / ms, 1.0), 4),
+                "how": "union of rank 0's conv grids' in-frame intervals (%globaltimer stamps), algorithmic FLOP of the pixels rank 0 outputs",
                 "alg_flop_per_launch_avg": weights.flops_per_pixel("base", 9) * my_px / max(conv_launches, 1),
                 "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 5)}
     line = {
@@ -458,11 +560,12 @@ def bench_main(args, rank, world, local_rank):
       "config": dict(B.workload_config(args, world), tiles="%dx%d of %dx%d, %d per rank" % (
         info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"], ntiles // world)),
       "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "frame_on_rank0": on_rank0,
+      "tile_plan_alternative": plan_alt, "large_unet_8k": large, "single_process_device": single,
       # all ranks: per tile the filter's ops + one autoexposure-bins launch, per rank one reduce
       "gpu_launches": K * (ntiles * (info["numOps"] + 1) + world), "clocks": clocks,
       "exchange": "every rank holds its tiles' inputs (tile + overlap); autoexposure: per-tile bin kernels + NCCL all-reduce of the "
                   "bin array (%d B) + fixed-order fold on every rank; output rectangles assembled in rank 0's buffer by copy-engine "
-                  "peer writes over NVLink (CUDA IPC); 4-byte all-reduce joins the frame; two frames in flight" % (4 * sets[0][2].nbins),
+                  "peer writes over NVLink (CUDA IPC); 4-byte all-reduce joins the frame; two frames in flight" % (4 * nbins),
     }
     print(json.dumps(line))
   host.release()

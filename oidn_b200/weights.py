@@ -59,15 +59,29 @@ _LAST_LAYER = {
 }
 
 
-def make_weights(kind, ic, seed=0):
-  """He-init weights N(0, 2/(9*cin)), biases U(0, 0.1), rounded to fp16 (what both sides consume)."""
+def make_weights(kind, ic, seed=0, passthrough=False):
+  """He-init weights N(0, 2/(9*cin)), biases U(0, 0.1), rounded to fp16 (what both sides consume).
+
+  passthrough=True: the last three convolutions additionally carry the first three input channels (the
+  main image in the transfer domain) straight to the three output channels -- centre tap 1 from the skip
+  connection of dec_conv1a, then channel i -> i -- with the rest of those rows scaled to a 2 % perturbation.
+  Every other layer keeps its random weights (and its full cost). The network then returns its input
+  plus a small perturbation, so a denoised constant-0.5 image stays inside the [0.1, 1] window the
+  reference's own test application checks with trained weights (apps/oidnTest.cpp:465-474): these are the
+  blobs compiled into the reference build used for integration runs (tools/build_reference_cuda.sh)."""
   rng = np.random.Generator(np.random.PCG64(seed))
   out = {}
   layers = unet_layers(kind, ic)
   for idx, (name, cin, cout) in enumerate(layers):
     w = rng.standard_normal((cout, cin, 3, 3), dtype=np.float32) * np.float32(np.sqrt(2.0 / (9 * cin)))
     b = rng.random((cout,), dtype=np.float32) * np.float32(0.1)
-    if idx == len(layers) - 1:
+    if passthrough and idx >= len(layers) - 3:
+      first = idx == len(layers) - 3            # dec_conv1a: concat(upsampled, input) -> the input starts at cin - ic
+      for o in range(3):
+        w[o] *= np.float32(0.02 / max(1.0, float(np.abs(w[o]).sum())))
+        w[o, (cin - ic if first else 0) + o, 1, 1] = np.float32(1.0)
+        b[o] = np.float32(0.0)
+    elif idx == len(layers) - 1:
       scale, shift = _LAST_LAYER.get((kind, ic), (0.1, 0.35))
       w = w * np.float32(scale)
       b = b * np.float32(scale) + np.float32(shift)
@@ -143,5 +157,5 @@ def read_tza(blob):
   return out
 
 
-def model_tza(kind, ic, seed=0):
-  return write_tza(make_weights(kind, ic, seed))
+def model_tza(kind, ic, seed=0, passthrough=False):
+  return write_tza(make_weights(kind, ic, seed, passthrough))

@@ -3,7 +3,8 @@
 # /root/reference (its CMake project configure_file()s into the source dir, which is read-only) and copies the
 # BINARIES into baseline/_ref (git-ignored, travels to the GPU box). The reference's weights/*.tza are Git-LFS
 # pointers in this checkout, so synthetic TZA files of the same architectures (oidn_b200.weights.model_tza: the
-# byte sizes equal the LFS sizes) are placed in the copy's weights/ and compiled in as the built-in blobs.
+# byte sizes equal the LFS sizes; passthrough=True: the network returns its input plus a small perturbation, so the
+# output sanity window of apps/oidnTest.cpp holds) are placed in the copy's weights/ and compiled in as the built-in blobs.
 # The CPU device stays off: it needs ISPC + oneTBB, which this image does not have.
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
@@ -18,7 +19,7 @@ rt_ldr_calb_cnrm rt_ldr_calb_cnrm_small rt_nrm rt_nrm_large rtlightmap_hdr rtlig
 for n in names:
   kind = "small" if n.endswith("_small") else ("large" if n.endswith("_large") else "base")
   ic = 9 if ("alb_nrm" in n or "calb_cnrm" in n) else (6 if n.endswith("_alb") or "_alb_small" in n else 3)
-  open("/tmp/oidn_ref/weights/%s.tza" % n, "wb").write(weights.model_tza(kind, ic, seed=0))
+  open("/tmp/oidn_ref/weights/%s.tza" % n, "wb").write(weights.model_tza(kind, ic, seed=0, passthrough=True))
 PY
 cd $BLD
 cmake -G Ninja $SRC -DCMAKE_BUILD_TYPE=Release -DOIDN_DEVICE_CPU=OFF -DOIDN_DEVICE_CUDA=ON -DOIDN_DEVICE_CUDA_API=RuntimeStatic \
