@@ -271,6 +271,21 @@ def main():
     # when it is not folded into dec_conv0's epilogue; fixed up below from the per-op profile)
     launches = K * (2 + ntiles * info["numOps"])
 
+    # ---- where the frame's time goes -------------------------------------------------------------------------
+    # (1) in-frame conv intervals: every conv grid stamps %globaltimer when its first CTA gets past the wait for the
+    #     previous grid and when its last CTA exits (device parameter profile=2). Launches overlap through programmatic
+    #     dependent launch (prologues run under the previous grid's tail), so the frame's conv time is the UNION of
+    #     the intervals -- by construction not more than the frame (frames run one at a time in this pass)
+    dev.set("profile", 2)
+    f.execute(); f.profile()
+    for _ in range(K):
+      f.execute()
+    prof2 = f.profile()
+    conv_union_ms = sum(m for _, kind, _, m in prof2 if kind == 3) / K
+    conv_layers = {n: round(m / K, 4) for n, kind, _, m in prof2 if kind == 0}
+    conv_launches = sum(n for _, kind, n, _ in prof2 if kind == 0) // K
+    dev.set("profile", 0)
+
     # ---- the same frames for >= 3 s (the short run above is a burst at full clocks; this is the regime a stream
     # of frames settles in: power-capped clocks) -----------------------------------------------------------------
     n_long = max(K, int(3000.0 / ms) + 1)
@@ -286,18 +301,6 @@ def main():
     ms_long = l0.elapsed_time(l1) / n_long
     clocks_long = sampler.window(tl0, tl1)
 
-    # ---- where the frame's time goes -------------------------------------------------------------------------
-    # (1) in-frame conv intervals: every conv grid stamps %globaltimer at its first CTA's start and last CTA's end
-    #     (device parameter profile=2); launches overlap through programmatic dependent launch, so the frame's conv
-    #     time is the UNION of the intervals -- by construction not more than the frame
-    dev.set("profile", 2)
-    f.execute(); f.profile()
-    for _ in range(K):
-      f.execute()
-    prof2 = f.profile()
-    conv_union_ms = sum(m for _, kind, _, m in prof2 if kind == 3) / K
-    conv_layers = {n: round(m / K, 4) for n, kind, _, m in prof2 if kind == 0}
-    conv_launches = sum(n for _, kind, n, _ in prof2 if kind == 0) // K
     # (2) CUDA events around every op (serialises the launches: used for the elementwise passes only)
     dev.set("profile", 1)
     f.execute(); f.profile()

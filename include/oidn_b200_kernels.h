@@ -95,8 +95,9 @@ OIDNB200_API int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv
 OIDNB200_API int oidnb200_conv_set_trace(oidnb200_conv* conv, void* trace_counters);
 
 /* In-frame timing: `stamps` = device array of 2 x uint64 {UINT64_MAX, 0} (or NULL to switch off). Every launch
- * then records min(start) / max(end) over its CTAs in %globaltimer nanoseconds -- when the grid really ran inside
- * a frame whose launches overlap (programmatic dependent launch), which CUDA events around a launch cannot show. */
+ * then records, in %globaltimer nanoseconds, the earliest moment one of its CTAs got past the wait for the
+ * previous grid (griddepcontrol.wait: its first activation load) and the latest CTA exit -- when the grid really ran
+ * inside a frame whose launches overlap (programmatic dependent launch), which CUDA events around a launch serialise. */
 OIDNB200_API int oidnb200_conv_set_stamps(oidnb200_conv* conv, void* stamps);
 
 /* ------------------------------------------------------------------------------------------

@@ -749,20 +749,33 @@ void UNetFilter::submitFrameStaged(const std::shared_ptr<ProgressState>& progres
         checkCuda(cudaMemcpy2DAsync(sl.in[k], S.inPitch[k], src, im.rowStride, (size_t)t.W1 * im.pixelStride, t.H1,
                                     cudaMemcpyDefault, in), "cudaMemcpy2DAsync (tile copy-in)");
       }
-      if (autoScale)
+      checkCuda(cudaEventRecord(ce(sl.evIn), in), "cudaEventRecord");
+    }
+  }
+
+  // ---- autoexposure bins of the tiles as they land (compute streams: the copy-in stream carries copies only)
+  if (autoScale)
+    for (int e = 0; e < E; ++e)
+    {
+      Engine* eng = device->getEngine(e);
+      eng->makeCurrent();
+      cudaStream_t comp = cs(eng->getAuxStream(Engine::Compute));
+      const size_t T = S.tilesOf[e].size();
+      for (size_t j = 0; j < T; ++j)
       {
+        const TileRect& t = tiles[S.tilesOf[e][j]];
+        Slot& sl = S.slots[e][par * T + j];
+        checkCuda(cudaStreamWaitEvent(comp, ce(sl.evIn), 0), "cudaStreamWaitEvent");
         // bins whose first pixel lies in the tile's destination rectangle: these rectangles partition the bin
         // grid, and a bin (<= 16 px) never leaves the source rectangle (overlap >= 96 px at interior edges)
         const int bh0 = firstBinAtOrAfter(t.hDst, nbh, color.H), bh1 = firstBinAtOrAfter(t.hDst + t.H2, nbh, color.H);
         const int bw0 = firstBinAtOrAfter(t.wDst, nbw, color.W), bw1 = firstBinAtOrAfter(t.wDst + t.W2, nbw, color.W);
         const Image v = virtualImage(color, sl.in[0], S.inPitch[0], t.hSrc, t.wSrc);
         const oidnb200_image vi{v.ptr, (int)v.format, v.W, v.H, v.pixelStride, v.rowStride};
-        checkABI(oidnb200_autoexposure_bins_launch(&vi, bh0, bh1, bw0, bw1, S.bins[par], in), "autoexposure bins");
+        checkABI(oidnb200_autoexposure_bins_launch(&vi, bh0, bh1, bw0, bw1, S.bins[par], comp), "autoexposure bins");
       }
-      checkCuda(cudaEventRecord(ce(sl.evIn), in), "cudaEventRecord");
+      checkCuda(cudaEventRecord(ce(S.evBins[par][e]), comp), "cudaEventRecord");
     }
-    if (autoScale) checkCuda(cudaEventRecord(ce(S.evBins[par][e]), in), "cudaEventRecord");
-  }
 
   // ---- input scale (core/unet_filter.cpp:172-189)
   if (autoScale)

@@ -112,7 +112,7 @@ struct ConvKernelParams
   int      relu, post_op;
   const float* bias;                // fp32 [CoutAlloc]
   unsigned long long* trace;        // [12 warps][16 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
-  unsigned long long* stamps;       // non-null: {min over CTAs of the start, max over CTAs of the end} in %globaltimer
+  unsigned long long* stamps;       // non-null: {min over CTAs of "past griddepcontrol.wait", max over CTAs of the exit} in %globaltimer
                                     // nanoseconds (two atomics per CTA): when the grid really ran inside a frame whose
                                     // launches overlap through programmatic dependent launch (bench.py's conv time)
   FusedOutput fo;                   // fo.enabled: the epilogue writes the output image instead of the tensor

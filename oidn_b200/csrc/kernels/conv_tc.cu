@@ -537,7 +537,6 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();   // this CTA's resources are the gate for the next grid's CTAs anyway
-  if (p.stamps && threadIdx.x == 0) atomicMin(&p.stamps[0], globaltimer_ns());
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + SmemLayout::tmem_ptr);
 
   // Both single-issuer roles keep warp-uniform control flow (all 32 lanes walk the loops, one
@@ -568,6 +567,8 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
         // dependent launch): everything above touched only weights; activations written by that
         // kernel are first read here, and this kernel's stores are ordered after these loads.
         pdl_wait();
+        // in-frame start stamp: the prerequisite grid has completed, this grid's first activation load follows
+        if (p.stamps && st == 0 && leader) atomicMin(&p.stamps[0], globaltimer_ns());
         uint32_t s = 0, ph = 0;
         const int PF = p.prefetch_rows;
         for (int item = vcta; item < nitems; item += nv)
