@@ -330,10 +330,10 @@ def single_process_device(args, torch, world, tza, host, K, Wm):
   f.set_image("output", out)
   f.set("hdr", True); f.set("quality", api.QUALITY_HIGH); f.set_data("weights", tza)
   f.commit()
-  info = f.info()
   for _ in range(Wm):
     f.execute_async()
   dev.sync()
+  info = f.info()
   with torch.cuda.device(0):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
@@ -535,12 +535,19 @@ def bench_main(args, rank, world, local_rank):
   # library stages every engine's tiles over NVLink (frame in GPU 0's HBM) or over each GPU's PCIe link (frame in
   # pinned host memory) and exchanges the autoexposure bins through peer stores. The other ranks idle at a barrier.
   single = None
-  dist.barrier()
-  if rank == 0 and not args.no_single_process:
-    try:
-      single = single_process_device(args, torch, world, tza, host, K, max(Wm, 2))
-    except Exception as e:  # noqa: BLE001
-      single = {"error": str(e)[:300]}
+  torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+  # the other ranks wait on the rendezvous store (host side): an NCCL barrier would park a spinning kernel on
+  # their GPUs, which rank 0 is about to use
+  store = dist.distributed_c10d._get_default_store()
+  if rank == 0:
+    if not args.no_single_process:
+      try:
+        single = single_process_device(args, torch, world, tza, host, K, max(Wm, 2))
+      except Exception as e:  # noqa: BLE001
+        single = {"error": str(e)[:300]}
+    store.set("oidnb200_single_process_done", "1")
+  else:
+    store.wait(["oidnb200_single_process_done"])
   dist.barrier()
 
   if rank == 0:
