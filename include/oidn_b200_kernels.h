@@ -94,6 +94,20 @@ OIDNB200_API int oidnb200_conv_get_info(const oidnb200_conv* conv, oidnb200_conv
  * role, the cycles spent blocked at each barrier (tools/probe_conv --trace). No effect otherwise. */
 OIDNB200_API int oidnb200_conv_set_trace(oidnb200_conv* conv, void* trace_counters);
 
+/* Two chained convolutions B(A(x)) as ONE launch: the tensor between them stays in shared memory (no HBM write /
+ * re-read). For the UNet's full-resolution pairs enc_conv0 -> enc_conv1 (+pool) and dec_conv1b -> dec_conv0 (+output
+ * process) (core/unet_filter.cpp:468-531). `a` and `b` are ordinary conv ops (created, weights packed, bound as
+ * usual; they must outlive the pair): the pair takes A's source / weights / bias and B's weights / bias / destination /
+ * fused output process from them. create returns OIDNB200_ERR_UNSUPPORTED when the shapes are not covered (plain
+ * 3x3 convs, A: <= 64 input and 32 or 64 output channels, B: <= 64 output channels, optional pool) -- the caller then
+ * simply launches the two convs. The result is bit-identical to the two launches. */
+typedef struct oidnb200_conv_pair oidnb200_conv_pair;
+OIDNB200_API int oidnb200_conv_pair_create(const oidnb200_conv* a, const oidnb200_conv* b, oidnb200_conv_pair** out);
+OIDNB200_API void oidnb200_conv_pair_destroy(oidnb200_conv_pair* pair);
+OIDNB200_API int oidnb200_conv_pair_bind(oidnb200_conv_pair* pair);   /* after (re)binding either conv */
+OIDNB200_API int oidnb200_conv_pair_launch(oidnb200_conv_pair* pair, oidnb200_stream stream);
+OIDNB200_API int oidnb200_conv_pair_get_info(const oidnb200_conv_pair* pair, oidnb200_conv_info* info);
+
 /* In-frame timing: `stamps` = device array of 2 x uint64 {UINT64_MAX, 0} (or NULL to switch off). Every launch
  * then records, in %globaltimer nanoseconds, the earliest moment one of its CTAs got past the wait for the
  * previous grid (griddepcontrol.wait: its first activation load) and the latest CTA exit -- when the grid really ran

@@ -70,6 +70,11 @@ KERNEL_ABI = {
                                                  C.POINTER(Image)]),
   "oidnb200_conv_launch_simt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
   "oidnb200_conv_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "oidnb200_conv_pair_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+  "oidnb200_conv_pair_destroy": (None, [C.c_void_p]),
+  "oidnb200_conv_pair_bind": (C.c_int, [C.c_void_p]),
+  "oidnb200_conv_pair_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "oidnb200_conv_pair_get_info": (C.c_int, [C.c_void_p, C.POINTER(ConvInfo)]),
   "oidnb200_conv_set_stamps": (C.c_int, [C.c_void_p, C.c_void_p]),
   "oidnb200_conv_get_info": (C.c_int, [C.c_void_p, C.POINTER(ConvInfo)]),
   "oidnb200_input_process_launch": (C.c_int, [C.POINTER(Image), C.POINTER(Image), C.POINTER(Image), C.POINTER(Tile),

@@ -34,6 +34,7 @@ Device::Device(const std::vector<int>& ids, const std::vector<void*>& streams)
   if (const char* e = getenv("OIDN_B200_MAX_TILE_PIXELS")) maxTilePixels = atol(e);
   if (const char* e = getenv("OIDN_B200_GRAPH")) graph = atoi(e);
   if (const char* e = getenv("OIDN_B200_STAGING")) staging = atoi(e);
+  if (const char* e = getenv("OIDN_B200_FUSE_PAIRS")) fusePairs = atoi(e);
   if (const char* e = getenv("OIDN_B200_WEIGHTS_DIR")) weightsDir = e;
   if (const char* e = getenv("OIDN_VERBOSE")) verbose = atoi(e);
 }
@@ -154,6 +155,7 @@ void Device::setInt(const std::string& name, int value)
   else if (name == "graph") graph = value;                 // backend specific: 1 = replay frames as a CUDA graph (frame streams)
   else if (name == "fuseOutput") fuseOutput = value;       // backend specific: 1 = output process inside the last conv's epilogue
   else if (name == "tilePolicy") tilePolicy = value;       // backend specific: 0 = reference search, 1 = fewest recomputed pixels
+  else if (name == "fusePairs") fusePairs = value;         // backend specific: 1 = conv -> conv pairs as one launch (kernels/conv_pair_tc.cu)
   else if (name == "staging") staging = value;             // backend specific: tile staging, see UNetFilter::wantStaging
   else if (committed) throw Exception(Error::InvalidOperation, "device can be committed only once");
   else throw Exception(Error::InvalidArgument, "unknown device parameter or type mismatch: '" + name + "'");
@@ -174,6 +176,7 @@ int Device::getInt(const std::string& name) const
   if (name == "graph") return graph;
   if (name == "fuseOutput") return fuseOutput;
   if (name == "staging") return staging;
+  if (name == "fusePairs") return fusePairs;
   if (name == "systemMemorySupported" || name == "managedMemorySupported")
   {
     int v = 0;

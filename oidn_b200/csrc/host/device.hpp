@@ -81,6 +81,7 @@ private:
   int fuseOutput = 1;
   int graph = 0;
   int staging = -1;
+  int fusePairs = 1;
   std::map<void*, size_t> hostMaps; // interleaved host allocations (mmap + cudaHostRegister): ptr -> bytes
   std::string weightsDir;
   std::mutex mutex;

@@ -188,6 +188,35 @@ oidnb200_conv_info Conv::getInfo() const
   return i;
 }
 
+std::unique_ptr<ConvPair> ConvPair::tryCreate(Conv& a, Conv& b)
+{
+  oidnb200_conv_pair* h = nullptr;
+  const int rc = oidnb200_conv_pair_create(a.getHandle(), b.getHandle(), &h);
+  if (rc == OIDNB200_ERR_UNSUPPORTED) return nullptr;
+  checkABI(rc, "conv pair");
+  std::unique_ptr<ConvPair> p(new ConvPair());
+  p->a = &a; p->b = &b; p->handle = h;
+  return p;
+}
+
+ConvPair::~ConvPair() { if (handle) oidnb200_conv_pair_destroy(handle); }
+
+void ConvPair::submit()
+{
+  if (!a->isBound()) a->finalize();
+  if (!b->isBound()) b->finalize();
+  checkABI(oidnb200_conv_pair_bind(handle), "conv pair bind"); // cheap: copies the tensor maps of the two bound convs
+  checkABI(oidnb200_conv_pair_launch(handle, a->getEngine()->getStream()),
+           ("conv pair '" + a->getName() + "' + '" + b->getName() + "'").c_str());
+}
+
+oidnb200_conv_info ConvPair::getInfo() const
+{
+  oidnb200_conv_info i{};
+  oidnb200_conv_pair_get_info(handle, &i);
+  return i;
+}
+
 void Pool::submitKernels()
 {
   checkABI(oidnb200_pool_launch(src, srcDesc.H, srcDesc.W, srcDesc.paddedC(), dst, engine->getStream()), "pool");

@@ -84,6 +84,8 @@ public:
   void submitKernels() override;
   oidnb200_conv_info getInfo() const;
   oidnb200_conv* getHandle() const { return handle; }
+  Engine* getEngine() const { return engine; }
+  bool isBound() const { return bound; }
 
 private:
   Engine* engine;
@@ -92,6 +94,23 @@ private:
   const void *src1 = nullptr, *src2 = nullptr, *weight = nullptr, *bias = nullptr;
   void* dst = nullptr;
   bool bound = false;
+};
+
+// Two chained convs as one launch (kernels/conv_pair_tc.cu): the tensor between them stays in shared memory.
+// Built by the graph over two Conv ops it keeps (they own weights and bindings); submit() of the pair replaces
+// the two launches.
+class ConvPair
+{
+public:
+  // nullptr when the kernel does not cover the two shapes
+  static std::unique_ptr<ConvPair> tryCreate(Conv& a, Conv& b);
+  ~ConvPair();
+  void submit();
+  oidnb200_conv_info getInfo() const;
+private:
+  ConvPair() = default;
+  Conv* a = nullptr; Conv* b = nullptr;
+  oidnb200_conv_pair* handle = nullptr;
 };
 
 class Pool : public Op

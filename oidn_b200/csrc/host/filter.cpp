@@ -320,7 +320,7 @@ std::vector<uint64_t> UNetFilter::frameKey() const
   k.push_back(bits);
   k.push_back((uint64_t)(uintptr_t)inputScaleDevPtr);
   k.push_back(((uint64_t)(uint32_t)numShards << 32) | (uint32_t)shardIndex);
-  k.push_back((uint64_t)device->getInt("fuseOutput"));
+  k.push_back((uint64_t)device->getInt("fuseOutput") | ((uint64_t)device->getInt("fusePairs") << 1));
   return k;
 }
 
@@ -823,6 +823,7 @@ void UNetFilter::submitFrameStaged(const std::shared_ptr<ProgressState>& progres
         inst.outputProcess->setDst(virtualImage(output, sl.out, S.outPitch, t.hDst, t.wDst));
         inst.graph->setProfiling(profiling);
         inst.graph->setFuseOutput(device->getInt("fuseOutput") != 0);
+        inst.graph->setFusePairs(device->getInt("fusePairs") != 0);
         inst.graph->setOpCallback(progress ? std::function<void()>([&, eng]() { report(eng); }) : std::function<void()>());
         inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
         inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);
@@ -924,6 +925,7 @@ void UNetFilter::submitFrame(const std::shared_ptr<ProgressState>& progress)
     Instance& inst = instances[tileIndex % numEngines];
     inst.graph->setProfiling(profiling);
     inst.graph->setFuseOutput(device->getInt("fuseOutput") != 0);
+    inst.graph->setFusePairs(device->getInt("fusePairs") != 0);
     inst.graph->setOpCallback(progress ? std::function<void()>([&, eng]() { report(eng); }) : std::function<void()>());
     inst.inputProcess->setTile(t.hSrc, t.wSrc, t.hBuf, t.wBuf, t.H1, t.W1);
     inst.outputProcess->setTile(t.hOutBuf, t.wOutBuf, t.hDst, t.wDst, t.H2, t.W2);

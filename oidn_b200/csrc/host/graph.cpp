@@ -13,6 +13,7 @@ Graph::~Graph() { clear(); }
 
 void Graph::clear()
 {
+  pairs.clear();
   ops.clear(); nodes.clear(); convs.clear();
   inputProcess.reset(); outputProcess.reset(); outputConv.reset();
   inputNode = outputSrcNode = -1;
@@ -190,6 +191,22 @@ void Graph::finalize()
   }
   if (inputProcess) inputProcess->setDst(ptrOf(inputNode));
   if (outputProcess) outputProcess->setSrc(ptrOf(outputSrcNode));
+
+  // conv -> conv pairs: B is a plain conv reading only A's tensor, and nothing else reads that tensor
+  pairs.clear();
+  for (size_t i = 0; i + 1 < convs.size(); ++i)
+  {
+    const ConvRecord& A = convs[i];
+    const ConvRecord& B = convs[i + 1];
+    if (B.src1 != A.dst || B.src2 >= 0 || A.src2 >= 0) continue;
+    int readers = outputSrcNode == A.dst ? 1 : 0;
+    for (const ConvRecord& r : convs) readers += (r.src1 == A.dst) + (r.src2 == A.dst);
+    if (readers != 1) continue;
+    if (!pairs.empty() && pairs.back().opB == nodes[A.dst].opID) continue; // a conv belongs to one pair only
+    auto pr = ConvPair::tryCreate(*A.conv, *B.conv);
+    if (!pr) continue;
+    pairs.push_back(PairRecord{nodes[A.dst].opID, nodes[B.dst].opID, std::move(pr)});
+  }
   finalized = true;
 }
 
@@ -217,11 +234,21 @@ void Graph::submit()
                                profiling == 2 ? static_cast<unsigned long long*>(stampBuf) + 2 * i : nullptr);
     if (profiling != 2) { engine->wait(); engine->free(stampBuf); stampBuf = nullptr; }
   }
+  // a fused pair replaces the launches of its two convs: A is skipped, the pair runs in B's place
+  auto submitOp = [&](size_t i) {
+    if (fusePairs)
+      for (const PairRecord& pr : pairs)
+      {
+        if ((int)i == pr.opA) return;
+        if ((int)i == pr.opB) { pr.pair->submit(); return; }
+      }
+    ops[i]->submit();
+  };
   if (profiling != 1)
   {
-    for (auto& op : ops)
+    for (size_t i = 0; i < ops.size(); ++i)
     {
-      if (!(fused && op == outputProcess)) op->submit();
+      if (!(fused && ops[i] == outputProcess)) submitOp(i);
       if (opCallback) opCallback();
     }
     if (profiling == 2) collectStamps();
@@ -235,7 +262,7 @@ void Graph::submit()
     checkCuda(cudaEventCreate(&e0), "cudaEventCreate");
     checkCuda(cudaEventCreate(&e1), "cudaEventCreate");
     cudaEventRecord(e0, st);
-    ops[i]->submit();
+    submitOp(i);
     cudaEventRecord(e1, st);
     stamps.push_back(Stamp{(int)i, e0, e1});
     if (opCallback) opCallback();

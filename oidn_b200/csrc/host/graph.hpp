@@ -55,6 +55,11 @@ public:
   // Output process folded into the last conv's epilogue when the output image allows it (default on;
   // device parameter "fuseOutput"). Decided per submit(): it depends on the image set for the frame.
   void setFuseOutput(bool on) { fuseOutput = on; }
+  // Conv -> conv pairs whose intermediate tensor has no other reader run as one launch (kernels/conv_pair_tc.cu;
+  // device parameter "fusePairs", default on): enc_conv0 -> enc_conv1, dec_conv1b -> dec_conv0 and their
+  // counterparts in the small / large nets. Bit-identical to the two launches.
+  void setFusePairs(bool on) { fusePairs = on; }
+  int getNumPairs() const { return (int)pairs.size(); }
   void collectProfile(std::vector<OpTime>& out);
 
   const std::shared_ptr<InputProcess>& getInputProcess() const { return inputProcess; }
@@ -95,6 +100,9 @@ private:
   int inputNode = -1, outputSrcNode = -1;
   std::shared_ptr<Conv> outputConv;   // producer of the output process's source, if it is a conv
   bool fuseOutput = true;
+  bool fusePairs = true;
+  struct PairRecord { int opA, opB; std::unique_ptr<ConvPair> pair; };
+  std::vector<PairRecord> pairs;
   ArenaPlanner planner;
   bool planned = false, finalized = false;
   size_t privateByteSize = 0;

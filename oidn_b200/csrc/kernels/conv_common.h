@@ -118,4 +118,38 @@ struct ConvKernelParams
   FusedOutput fo;                   // fo.enabled: the epilogue writes the output image instead of the tensor
 };
 
+// ---- two chained convolutions in one kernel (conv_pair_tc.cu) ------------------------------------------------------
+constexpr int kPairStrip     = 126;  // output pixels of conv B per work-item row (conv A computes 128: one halo pixel each side)
+constexpr int kPairThreads   = 704;  // 2 x (TMA + A-MMA warp) + 2 x 4 A-epilogue warps + 2 x 4 B-epilogue warps + 2 B-MMA warps
+constexpr int kPairMaxStages = 16;   // input ring stages per stream
+constexpr int kPairMaxMid    = 8;    // mid ring stages per stream
+
+struct PairKernelParams
+{
+  CUtensorMap amap;                 // conv A's source (3D, box {ccA, 130, 1})
+  CUtensorMap wmapA, wmapB;         // packed weights of A and B (4D, box {cc, Cout, 3, 1})
+  int      H, W;
+  int      ccA;                     // A's input channels (padded; one K chunk: 16, 32 or 64)
+  int      CA;                      // A's output = B's input channels (32 or 64)
+  int      CB;                      // B's padded output channels (16 .. 64)
+  int      poolB, reluA, reluB;
+  int      nstreams;                // 1 or 2
+  int      RA, RB;                  // TMEM accumulator ring slots of A / B per stream
+  int      NA, NM;                  // input ring / mid ring stages per stream
+  int      RC, nstrips, nrowchunks; // rows per work item, strips of kPairStrip pixels, row chunks
+  uint32_t a_stage_bytes, mid_stage_bytes;
+  uint32_t wA_blk, wB_blk;          // bytes of one kw block of A's / B's resident weights
+  uint32_t wB_off;                  // B's weights inside the weight region
+  uint32_t w_bytes;                 // bytes TMA-loaded per CTA (both convs)
+  uint32_t w_bytes_smem;            // size of the weight region (1024-aligned)
+  uint32_t hiA, hiB;                // high words of the UMMA descriptors (rows of ccA*2 / CA*2 bytes)
+  const float* biasA;
+  const float* biasB;
+  void*    out_ptr;                 // B's destination tensor [Hd][Wd][CoutPadB] fp16
+  int      out_W, CoutPadB;
+  unsigned long long* stamps;       // as ConvKernelParams::stamps
+  unsigned long long* trace;        // [22 warps][16 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
+  FusedOutput fo;                   // fo.enabled: B's epilogue writes the output image instead of the tensor
+};
+
 } // namespace oidnb200

@@ -16,6 +16,7 @@
 namespace oidnb200 {
 
 cudaError_t conv3x3_tc_launch(const ConvKernelParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t conv3x3_pair_launch(const PairKernelParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // Driver entry point for tensor-map encoding (no link-time libcuda dependency, so the library
@@ -490,7 +491,156 @@ struct oidnb200_conv
   std::unique_ptr<ConvPlan> fused_plan;
 };
 
+// Two chained convs as one launch (conv_pair_tc.cu). Refers to the two single-conv ops, which own descriptors,
+// packed weights and bindings.
+struct oidnb200_conv_pair
+{
+  const oidnb200_conv* a = nullptr;
+  const oidnb200_conv* b = nullptr;
+  PairKernelParams kp;
+  int grid = 0;
+  size_t smem = 0;
+  bool bound = false;
+};
+
+static int pair_plan(const oidnb200_conv_desc& da, const ConvPlan& A, const oidnb200_conv_desc& db, const ConvPlan& B,
+                     oidnb200_conv_pair& pr)
+{
+  auto no = [](const char* why) { set_error(std::string("conv pair: ") + why); return OIDNB200_ERR_UNSUPPORTED; };
+  if (getenv("OIDN_B200_NO_PAIRS")) return no("disabled by OIDN_B200_NO_PAIRS");
+  if (da.H != db.H || da.W != db.W) return no("resolutions differ");
+  if (da.C2 != 0 || db.C2 != 0 || da.src1_upsampled || db.src1_upsampled) return no("concat / upsampled sources are not fused");
+  if (da.post_op != POST_NONE || (db.post_op != POST_NONE && db.post_op != POST_POOL)) return no("post-op not supported");
+  if (A.kp.nchunks != 1 || B.kp.nchunks != 1 || A.kp.ngroups != 1 || B.kp.ngroups != 1) return no("more than one K chunk / channel group");
+  if (db.C1 != da.Cout || (da.Cout != 32 && da.Cout != 64) || db.Cout > 64) return no("channel counts not covered");
+  PairKernelParams& kp = pr.kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.H = da.H; kp.W = da.W;
+  kp.ccA = da.C1; kp.CA = da.Cout; kp.CB = db.Cout;
+  kp.poolB = db.post_op == POST_POOL; kp.reluA = da.relu; kp.reluB = db.relu;
+  kp.a_stage_bytes = align_up(130u * kp.ccA * 2u, 1024);
+  kp.mid_stage_bytes = align_up(130u * kp.CA * 2u, 1024);
+  kp.wA_blk = 3u * kp.CA * kp.ccA * 2u;
+  kp.wB_blk = 3u * kp.CB * kp.CA * 2u;
+  if (kp.wA_blk % 1024 || kp.wB_blk % 1024) return no("weight blocks are not 1024-byte multiples");
+  kp.wB_off = 3u * kp.wA_blk;
+  kp.w_bytes = 3u * (kp.wA_blk + kp.wB_blk);
+  kp.w_bytes_smem = align_up(kp.w_bytes, 1024);
+  kp.hiA = A.kp.chunk_hi[0];
+  kp.hiB = B.kp.chunk_hi[0];
+  const uint32_t avail = kSmemBudget - 1024 - kSmemHeader - kp.w_bytes_smem;
+  // Streams x accumulator rings x shared-memory rings (measured on the 4K shapes, tools/run_probe_pair_sweep.sh,
+  // profiles/r02_probe_pair_sweep.log: two streams beat one deep stream by 4-6 %; a pooling B wants one more slot
+  // than A -- its epilogue drains two rows at a time -- so A runs on three; ring depths beyond that change < 1 %).
+  // OIDN_B200_PAIR_{STREAMS,RA,RB,NM,NA} override (hardware probing only).
+  auto envi = [](const char* n, int dflt) { const char* e = getenv(n); return e ? atoi(e) : dflt; };
+  int nst = 0;
+  for (int cand = envi("OIDN_B200_PAIR_STREAMS", 2); cand >= 1 && !nst; --cand)
+  {
+    const int cols = kTmemCols / cand;
+    int ra = envi("OIDN_B200_PAIR_RA", (cand == 2 && (kp.poolB || kp.CA == 64)) ? 3 : 4);
+    int rb = std::min(envi("OIDN_B200_PAIR_RB", 8), (cols - ra * kp.CA) / kp.CB);
+    if (rb < 4) continue;
+    for (int nm = envi("OIDN_B200_PAIR_NM", 4); nm >= 3 && !nst; --nm)
+    {
+      const long left = (long)avail / cand - (long)nm * kp.mid_stage_bytes;
+      const int na = (int)std::min<long>(envi("OIDN_B200_PAIR_NA", kPairMaxStages), left / (long)kp.a_stage_bytes);
+      if (na >= 3) { nst = cand; kp.nstreams = cand; kp.RA = ra; kp.RB = rb; kp.NM = nm; kp.NA = na; }
+    }
+  }
+  if (!nst) return no("accumulator / shared-memory rings do not fit");
+  pr.smem = 1024 + kSmemHeader + kp.w_bytes_smem + (size_t)nst * ((size_t)kp.NA * kp.a_stage_bytes + (size_t)kp.NM * kp.mid_stage_bytes);
+  kp.nstrips = (da.W + kPairStrip - 1) / kPairStrip;
+  const int P = num_sms() * nst;
+  const int step = kp.poolB ? 2 : 1;
+  int bestRC = step; long bestCost = -1;
+  for (int RC = step; RC <= da.H + step - 1; RC += step)
+  {
+    const long items = (long)kp.nstrips * ((da.H + RC - 1) / RC);
+    const long waves = (items + P - 1) / P;
+    const long cost = waves * (RC + 4);
+    if (bestCost < 0 || cost < bestCost || (cost == bestCost && RC > bestRC)) { bestCost = cost; bestRC = RC; }
+  }
+  kp.RC = bestRC;
+  kp.nrowchunks = (da.H + bestRC - 1) / bestRC;
+  const int items = kp.nstrips * kp.nrowchunks;
+  pr.grid = std::min(num_sms(), (items + nst - 1) / nst);
+  return 0;
+}
+
 extern "C" {
+
+int oidnb200_conv_pair_create(const oidnb200_conv* a, const oidnb200_conv* b, oidnb200_conv_pair** out)
+{
+  if (!a || !b || !out)
+  {
+    set_error("conv_pair_create: null argument");
+    return OIDNB200_ERR_INVALID;
+  }
+  oidnb200_conv_pair* pr = new oidnb200_conv_pair();
+  pr->a = a; pr->b = b;
+  const int rc = pair_plan(a->plan.desc, a->plan, b->plan.desc, b->plan, *pr);
+  if (rc)
+  {
+    delete pr;
+    return rc;
+  }
+  *out = pr;
+  return 0;
+}
+
+void oidnb200_conv_pair_destroy(oidnb200_conv_pair* pair) { delete pair; }
+
+int oidnb200_conv_pair_bind(oidnb200_conv_pair* pr)
+{
+  const ConvPlan& A = pr->a->plan;
+  const ConvPlan& B = pr->b->plan;
+  if (!A.bound || !B.bound)
+  {
+    set_error("conv_pair_bind: both convolutions must be bound first");
+    return OIDNB200_ERR_INVALID;
+  }
+  PairKernelParams& kp = pr->kp;
+  kp.amap = A.kp.amap[0];
+  kp.wmapA = A.kp.wmap[0];
+  kp.wmapB = B.kp.wmap[0];
+  kp.biasA = A.kp.bias;
+  kp.biasB = B.kp.bias;
+  kp.out_ptr = B.kp.out_ptr;
+  kp.out_W = B.kp.out_W;
+  kp.CoutPadB = B.kp.CoutPad;
+  pr->bound = true;
+  return 0;
+}
+
+int oidnb200_conv_pair_launch(oidnb200_conv_pair* pr, oidnb200_stream stream)
+{
+  if (!pr->bound)
+  {
+    set_error("conv_pair_launch: op not bound");
+    return OIDNB200_ERR_INVALID;
+  }
+  pr->kp.fo = pr->b->plan.kp.fo;            // conv B's fused output process (oidnb200_conv_set_output_process)
+  pr->kp.stamps = pr->b->plan.kp.stamps;    // in-frame interval of the pair under conv B's entry
+  pr->kp.trace = pr->b->plan.kp.trace;
+  const cudaError_t e = conv3x3_pair_launch(pr->kp, pr->grid, pr->smem, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+  {
+    set_error(std::string("conv_pair_launch: ") + cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int oidnb200_conv_pair_get_info(const oidnb200_conv_pair* pr, oidnb200_conv_info* info)
+{
+  memset(info, 0, sizeof(*info));
+  // ngroups / nchunks / out_nbuf carry the pair's own ring sizes: mid stages, A's accumulator slots
+  info->grid = pr->grid; info->smem_bytes = (int)pr->smem; info->ngroups = pr->kp.NM; info->cout_group = pr->kp.CB;
+  info->nchunks = pr->kp.RA; info->nstages = pr->kp.NA; info->ring_slots = pr->kp.RB; info->rows_per_item = pr->kp.RC;
+  info->nstrips = pr->kp.nstrips; info->nrowchunks = pr->kp.nrowchunks; info->nstreams = pr->kp.nstreams; info->out_nbuf = 0;
+  return 0;
+}
 
 int oidnb200_conv_create(const oidnb200_conv_desc* desc, oidnb200_conv** out)
 {

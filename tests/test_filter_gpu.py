@@ -418,3 +418,31 @@ def test_prefilter_pipeline_clean_aux(device, oracle):
     e, p = metrics(got, r)
     assert e <= MAX_ERR and p >= MIN_PSNR, ("beauty", e, p)
   fa.release(); fn.release(); fb.release()
+
+
+@pytest.mark.parametrize("kind,ic,params", [("base", 9, dict(hdr=True)), ("small", 3, dict(quality=api.QUALITY_FAST)),
+                                            ("large", 9, dict(hdr=True, cleanAux=True))], ids=["base", "small", "large"])
+def test_fused_conv_pairs_equal_separate_launches(kind, ic, params):
+  """Device parameter fusePairs (default on): enc_conv0 -> enc_conv1 and dec_conv1b -> dec_conv0 (and their
+  counterparts in the small / large nets) as one launch each == two launches each, bit for bit, single- and
+  multi-tile, with the output process in the pair's epilogue and as a separate pass."""
+  W, H = 1500, 900
+  tza = weights.model_tza(kind, ic, seed=0)
+  imgs = synth.benchmark_images(W, H, hdr=bool(params.get("hdr")), albedo=(ic == 9), normal=(ic == 9), seed=8)
+  dev = api.Device((0,)).commit()
+  res = {}
+  try:
+    for pairs in (1, 0):
+      dev.set("fusePairs", pairs)
+      for fuse_out in (1, 0):
+        dev.set("fuseOutput", fuse_out)
+        for tiled in (False, True):
+          extra = dict(maxMemoryMB=0) if tiled else {}
+          res[pairs, fuse_out, tiled], info = run_filter(dev, tza, imgs["color"], imgs.get("albedo"), imgs.get("normal"), **params, **extra)
+          assert (info["tileCountH"] * info["tileCountW"] > 1) == tiled
+  finally:
+    dev.release()
+  base = res[0, 0, False]
+  assert np.isfinite(base).all() and not np.any(base == -123.0)
+  for k, v in res.items():
+    np.testing.assert_array_equal(base.view(np.uint32), v.view(np.uint32), err_msg=str(k))

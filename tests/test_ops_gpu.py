@@ -335,3 +335,68 @@ def test_pool_upsample_image_copy(oracle):
     a, b = image_of(src), image_of(dstv)
     check(L.oidnb200_image_copy_launch(C.byref(a), C.byref(b), st))
     assert torch.equal(dstv, src) and float(big[:, :3].abs().sum()) == 0 and float(big[:, :, 3].abs().sum()) == 0
+
+
+# ---- conv pairs: B(A(x)) as one launch (kernels/conv_pair_tc.cu) ----------------------------------------------------
+# (H, W, I_A, C_A(out of A = in of B), O_B, poolB)
+PAIR_CASES = [
+  (16, 128, 9, 32, 32, 1),      # enc_conv0 -> enc_conv1 + pool
+  (38, 301 * 2, 9, 32, 32, 1),  # several strips of 126, ragged last strip
+  (2, 2, 9, 32, 32, 1),         # smallest poolable tile
+  (1, 1, 64, 32, 3, 0),
+  (33, 127, 64, 32, 3, 0),      # dec_conv1b -> dec_conv0: one pixel more than a strip
+  (40, 253, 32, 32, 3, 0),      # small net: dec_conv1b (32) -> dec_conv0
+  (24, 130, 9, 64, 64, 1),      # large net: enc_conv1a -> enc_conv1b + pool (one stream)
+  (21, 260, 64, 64, 3, 0),      # large net: dec_conv1b -> dec_conv1c
+  (300, 140, 64, 32, 3, 0),     # many row chunks
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=["%dx%d_%d_%d_%d_p%d" % c for c in PAIR_CASES])
+def test_conv_pair_bit_identical_to_two_launches(case):
+  """The fused pair keeps conv A's rows in shared memory (rounded to fp16 exactly as the stored tensor would have
+  been, zero outside the image: conv B's padding) -- every output bit must equal the two-launch path, which
+  test_conv_matches_oracle pins to the oracle."""
+  H, W, IA, CA, OB, pool = case
+  L = capi.lib()
+  rng = np.random.default_rng(hash(case) & 0xFFFF)
+  C1, Cb = -(-IA // 16) * 16, -(-OB // 16) * 16
+  s = np.zeros((H, W, C1), np.float16); s[:, :, :IA] = _rand_half(rng, (H, W, IA))
+  wa = (rng.standard_normal((CA, IA, 3, 3)) * np.sqrt(2.0 / (9 * IA))).astype(np.float16)
+  ba = (rng.random(CA) * 0.2 - 0.1).astype(np.float16)        # some channels go negative before the ReLU
+  wb = (rng.standard_normal((OB, CA, 3, 3)) * np.sqrt(2.0 / (9 * CA))).astype(np.float16)
+  bb = (rng.random(OB) * 0.2 - 0.1).astype(np.float16)
+  src = torch.from_numpy(s).cuda()
+  a = ConvOp(H, W, C1, 0, CA, relu=1)
+  mid = a.run(src, None, wa, ba, IA, 0)
+  b = ConvOp(H, W, CA, 0, Cb, relu=1, post_op=pool)
+  ref = b.run(mid, None, wb, bb, CA, 0)
+  # rebind B to a fresh destination and poison the tensor between the convs: the pair must not touch either
+  out = torch.full_like(ref, float("nan"))
+  dwb, dbb = b._keep
+  check(L.oidnb200_conv_bind(b.h, mid.data_ptr(), None, dwb.data_ptr(), dbb.data_ptr(), out.data_ptr()))
+  mid.fill_(float("nan"))
+  pair = C.c_void_p()
+  check(L.oidnb200_conv_pair_create(a.h, b.h, C.byref(pair)))
+  check(L.oidnb200_conv_pair_bind(pair))
+  check(L.oidnb200_conv_pair_launch(pair, torch.cuda.current_stream().cuda_stream))
+  torch.cuda.synchronize()
+  L.oidnb200_conv_pair_destroy(pair)
+  assert bool(torch.isnan(mid).all())
+  assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+
+
+def test_conv_pair_rejects_what_it_does_not_cover():
+  L = capi.lib()
+  def pair_rc(da, db):
+    a, b = ConvOp(*da), ConvOp(*db)
+    p = C.c_void_p()
+    rc = L.oidnb200_conv_pair_create(a.h, b.h, C.byref(p))
+    if rc == 0:
+      L.oidnb200_conv_pair_destroy(p)
+    return rc
+  assert pair_rc((32, 128, 16, 0, 32), (32, 128, 32, 0, 32)) == 0
+  assert pair_rc((32, 128, 16, 0, 32), (32, 128, 32, 16, 32)) == -2          # concat B
+  assert pair_rc((32, 128, 96, 0, 96), (32, 128, 96, 0, 96)) == -2           # more than one K chunk / 96 channels
+  assert pair_rc((32, 128, 16, 0, 32), (16, 64, 32, 0, 32)) == -2            # different resolution
+  assert pair_rc((32, 128, 16, 0, 48), (32, 128, 48, 0, 32)) == -2           # A's output must be 32 or 64 channels

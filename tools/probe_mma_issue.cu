@@ -23,8 +23,19 @@ struct Result
   long long issue, done;
 };
 
+template <int KSTEPS, int SHIFT>
+__device__ __forceinline__ void issue_group(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+  // one staged row's worth of MMAs as the conv kernels issue them: 3 taps x KSTEPS k-steps, offsets are immediates
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k)
+      umma_f16(d, adesc + (uint64_t)(k * 2 + (SHIFT ? s * KSTEPS * 2 : 0)), bdesc + (uint64_t)(k * 2), idesc, (s | k) ? 1u : acc);
+}
+
 __global__ void __launch_bounds__(128, 1)
-mma_issue_kernel(int N, int issuers, int tiles, int count, Result* out)
+mma_issue_kernel(int N, int issuers, int tiles, int count, int row_bytes, int shift, Result* out)
 {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -60,17 +71,23 @@ mma_issue_kernel(int N, int issuers, int tiles, int count, Result* out)
     const uint32_t cols = 512u / (uint32_t)issuers;
     const uint32_t t0 = tmem_base + (uint32_t)warp * cols;
     const uint32_t idesc = umma_idesc_f16((uint32_t)N);
-    const uint64_t adesc = umma_desc(a_tile, 128, 0), bdesc = umma_desc(b_tile, 128, 0);
+    // row_bytes 128/64/32 = the swizzle mode of the layer's K chunk (64/32/16 channels); shift: the A operand starts
+    // 0, 1, 2 rows into the tile in turn (the conv kernels' horizontal taps are such shifted views of one staged row)
+    const uint64_t adesc = umma_desc(a_tile, (uint32_t)row_bytes, 0), bdesc = umma_desc(b_tile, (uint32_t)row_bytes, 0);
+    const int ksteps = row_bytes / 32;
     long long c0 = 0, c1 = 0, c2 = 0;
     __syncwarp();
     if (leader)
     {
       c0 = clock64();
-      for (int i = 0; i < count; ++i)
+      const int groups = count / (3 * ksteps);
+      for (int g = 0; g < groups; ++g)
       {
-        const uint32_t d = t0 + (uint32_t)(i % tiles) * (uint32_t)N;
-        // advance the K offset inside the 128-byte row like a real K loop does (4 k-steps of 32 bytes)
-        umma_f16(d, adesc + (uint64_t)((i & 3) * 2), bdesc + (uint64_t)((i & 3) * 2), idesc, i >= tiles ? 1u : 0u);
+        const uint32_t d = t0 + (uint32_t)(g % tiles) * (uint32_t)N;
+        const uint32_t acc = g >= tiles ? 1u : 0u;
+        if (ksteps == 4) { if (shift) issue_group<4, 1>(d, adesc, bdesc, idesc, acc); else issue_group<4, 0>(d, adesc, bdesc, idesc, acc); }
+        else if (ksteps == 2) { if (shift) issue_group<2, 1>(d, adesc, bdesc, idesc, acc); else issue_group<2, 0>(d, adesc, bdesc, idesc, acc); }
+        else { if (shift) issue_group<1, 1>(d, adesc, bdesc, idesc, acc); else issue_group<1, 0>(d, adesc, bdesc, idesc, acc); }
       }
       c1 = clock64();
       umma_commit(bar);
@@ -97,15 +114,19 @@ int main(int argc, char** argv)
 {
   if (argc < 5)
   {
-    printf("usage: probe_mma_issue <N 16..256, multiple of 16> <issuers 1..4> <tiles >= 1> <count>\n");
+    printf("usage: probe_mma_issue <N 16..256, multiple of 16> <issuers 1..4> <tiles >= 1> <count> [row_bytes 128|64|32] [shift 0|1]\n");
     return 1;
   }
-  const int N = atoi(argv[1]), issuers = atoi(argv[2]), tiles = atoi(argv[3]), count = atoi(argv[4]);
+  const int N = atoi(argv[1]), issuers = atoi(argv[2]), tiles = atoi(argv[3]);
+  int count = atoi(argv[4]);
+  const int row_bytes = argc > 5 ? atoi(argv[5]) : 128, shift = argc > 6 ? atoi(argv[6]) : 0;
   if (N < 16 || N > 256 || N % 16 || issuers < 1 || issuers > 4 || tiles < 1 || tiles * N > 512 / issuers || count < 1)
   {
     printf("bad arguments (tiles * N must fit 512 / issuers TMEM columns)\n");
     return 1;
   }
+  count = count / (3 * (row_bytes / 32)) * (3 * (row_bytes / 32));   // whole rows of 3 taps x k-steps
+  if (count < 1) { printf("count too small\n"); return 1; }
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const size_t smem = 1024 + 1024 + 4 * (16384 + 32768);
@@ -115,7 +136,7 @@ int main(int argc, char** argv)
   for (int rep = 0; rep < 3; ++rep)
   {
     cudaMemset(d, 0, sizeof(Result) * sms * 4);
-    mma_issue_kernel<<<sms, 128, smem>>>(N, issuers, tiles, count, d);
+    mma_issue_kernel<<<sms, 128, smem>>>(N, issuers, tiles, count, row_bytes, shift, d);
     const cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess)
     {
@@ -135,8 +156,8 @@ int main(int argc, char** argv)
       if (r.done > worst_done) worst_done = r.done;
     }
   const double floor_cycles = 128.0 * N / 256.0;   // tensor-pipe floor per MMA (B300_MICROARCH.md), one issuer
-  printf("N=%d issuers=%d tiles=%d count=%d | per MMA: issue %.1f cycles, done %.1f (min) .. %.1f (max) cycles | pipe floor %.1f x %d issuers = %.1f\n",
-         N, issuers, tiles, count, (double)best_issue / count, (double)best_done / count, (double)worst_done / count,
+  printf("N=%d issuers=%d tiles=%d count=%d rowB=%d shift=%d | per MMA: issue %.1f cycles, done %.1f (min) .. %.1f (max) cycles | pipe floor %.1f x %d issuers = %.1f\n",
+         N, issuers, tiles, count, row_bytes, shift, (double)best_issue / count, (double)best_done / count, (double)worst_done / count,
          floor_cycles, issuers, floor_cycles * issuers);
   cudaFree(d);
   return 0;
