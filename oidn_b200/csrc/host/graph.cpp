@@ -116,6 +116,17 @@ Graph::Value Graph::addConvImpl(const std::string& name, Value s1, Value s2, Act
   nodes.push_back(Node{dst, postOp == PostOp::Upsample, planner.newAlloc(opID, dst.byteSize()), opID});
   planner.addDep(opID, n1.allocID);
   if (concat) planner.addDep(opID, nodes.at(s2.id).allocID);
+  // A conv that may run fused with its producer (finalize(): ConvPair) reads the PRODUCER's source while it writes
+  // its own destination: that source must stay alive (and un-aliased) through this op.
+  if (!concat)
+    for (const ConvRecord& pr : convs)
+      if (pr.dst == s1.id && pr.src2 < 0)
+      {
+        const int ca = round_up(pr.conv->getDesc().outC, 16), c1 = pr.conv->getDesc().src1.paddedC();
+        if ((ca == 32 || ca == 64) && c1 <= 64 && round_up(d.outC, 16) <= 64 && !pr.conv->getDesc().src1Upsampled &&
+            pr.conv->getDesc().postOp == PostOp::None)
+          planner.addDep(opID, nodes.at(pr.src1).allocID);
+      }
 
   ConvRecord r;
   r.conv = conv; r.src1 = s1.id; r.src2 = s2.id; r.dst = (int)nodes.size() - 1;

@@ -26,6 +26,7 @@ constexpr int kSmemHeader  = 4096;  // barriers + TMEM pointer (3 KB) + bias (51
 constexpr int kTmemCols    = 512;
 constexpr int kMaxSlots    = 16;
 constexpr int kSmemBudget  = 232448; // 227 KB opt-in dynamic shared memory per CTA
+constexpr int kMaxBiasParams = 256; // output channels whose bias travels in the kernel parameters
 
 // Output-channel pieces of a group of nb*16 channels: 64-channel pieces, then 32, then 16 (the TMA
 // store box / swizzle widths). Shared by the planner (tensor maps) and the kernel (staging layout).
@@ -111,6 +112,12 @@ struct ConvKernelParams
   int      out_W;                   // Wd
   int      relu, post_op;
   const float* bias;                // fp32 [CoutAlloc]
+  // The same values inside the kernel parameters (constant bank) when the op knows them on the host
+  // (oidnb200_conv_pack_bias) and CoutAlloc <= kMaxBiasParams: the epilogue then reads its bias through the
+  // constant cache instead of shared memory, whose data pipe the tensor core's operand reads already fill on
+  // these layers (ncu: l1tex__data_pipe_{tc,lsu}_wavefronts_mem_shared).
+  int      bias_in_params;
+  float    bias_c[kMaxBiasParams];
   unsigned long long* trace;        // [12 warps][16 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
   unsigned long long* stamps;       // non-null: {min over CTAs of "past griddepcontrol.wait", max over CTAs of the exit} in %globaltimer
                                     // nanoseconds (two atomics per CTA): when the grid really ran inside a frame whose
@@ -145,6 +152,8 @@ struct PairKernelParams
   uint32_t hiA, hiB;                // high words of the UMMA descriptors (rows of ccA*2 / CA*2 bytes)
   const float* biasA;
   const float* biasB;
+  int      bias_in_params;          // as ConvKernelParams: biases of A and B in the constant bank
+  float    biasA_c[64], biasB_c[64];
   void*    out_ptr;                 // B's destination tensor [Hd][Wd][CoutPadB] fp16
   int      out_W, CoutPadB;
   unsigned long long* stamps;       // as ConvKernelParams::stamps

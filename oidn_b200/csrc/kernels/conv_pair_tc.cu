@@ -406,6 +406,7 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
       const uint32_t row_off = (uint32_t)pix * rowb;
       const uint32_t xr = ((row_off >> 7) & ((rowb >> 4) - 1u)) << 4;   // swizzle term of this row (16-B chunks)
       const bool relu = p.reluA != 0;
+      const bool cbias = p.bias_in_params != 0;   // bias through the constant bank: the shared-memory pipe is the bottleneck
       RingPos ring; ring.R = RA;
       uint32_t ms = 0, mph = 0;
       for (int item = vcta; item < nitems; item += nv)
@@ -434,7 +435,8 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
 #pragma unroll
             for (int i = 0; i < 16; ++i)
             {
-              const float2 s = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bias2[j / 2 + i]);
+              const float2 bv = cbias ? make_float2(p.biasA_c[j + 2 * i], p.biasA_c[j + 2 * i + 1]) : bias2[j / 2 + i];
+              const float2 s = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bv);
               const uint32_t hv = relu ? pack_half2_relu(s.x, s.y) : pack_half2(s.x, s.y);
               h[i] = inside ? hv : 0u;
             }
@@ -472,6 +474,7 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
       const float2* bias2 = reinterpret_cast<const float2*>(bias_s);
       const int pix = q * 32 + lane;                         // B pixel inside the strip: x = x0 + pix, valid for pix < 126
       const bool relu = p.reluB != 0;
+      const bool cbias = p.bias_in_params != 0;
       RingPos ring; ring.R = RB;
       if (p.fo.enabled)
       {
@@ -556,7 +559,8 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
 #pragma unroll
               for (int i = 0; i < 8; ++i)
               {
-                const float2 s = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bias2[j / 2 + i]);
+                const float2 bv = cbias ? make_float2(p.biasB_c[j + 2 * i], p.biasB_c[j + 2 * i + 1]) : bias2[j / 2 + i];
+                const float2 s = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bv);
                 h[i] = relu ? pack_half2_relu(s.x, s.y) : pack_half2(s.x, s.y);
               }
               if (pool)

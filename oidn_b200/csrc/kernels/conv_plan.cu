@@ -489,6 +489,8 @@ struct oidnb200_conv
   // 0.143 ms, while the UNfused conv is 7 % slower with four streams). So a conv that can be fused
   // keeps a second, four-stream plan that oidnb200_conv_launch uses while a fusion is set.
   std::unique_ptr<ConvPlan> fused_plan;
+  // the packed bias as oidnb200_conv_pack_bias produced it (host copy): goes into the kernel parameters at bind
+  mutable std::vector<float> host_bias;
 };
 
 // Two chained convs as one launch (conv_pair_tc.cu). Refers to the two single-conv ops, which own descriptors,
@@ -606,6 +608,13 @@ int oidnb200_conv_pair_bind(oidnb200_conv_pair* pr)
   kp.wmapB = B.kp.wmap[0];
   kp.biasA = A.kp.bias;
   kp.biasB = B.kp.bias;
+  kp.bias_in_params = 0;
+  if (A.kp.bias_in_params && B.kp.bias_in_params)
+  {
+    memcpy(kp.biasA_c, A.kp.bias_c, sizeof(float) * kp.CA);
+    memcpy(kp.biasB_c, B.kp.bias_c, sizeof(float) * kp.CB);
+    kp.bias_in_params = 1;
+  }
   kp.out_ptr = B.kp.out_ptr;
   kp.out_W = B.kp.out_W;
   kp.CoutPadB = B.kp.CoutPad;
@@ -712,6 +721,7 @@ int oidnb200_conv_pack_bias(const oidnb200_conv* conv, const uint16_t* b_x, int 
   }
   float* dst = static_cast<float*>(dst_bias);
   for (int o = 0; o < pl.CoutAlloc; ++o) dst[o] = o < O ? half_bits_to_float(b_x[o]) : 0.f;
+  conv->host_bias.assign(dst, dst + pl.CoutAlloc);   // bind() copies it into the kernel parameters
   return 0;
 }
 
@@ -719,7 +729,21 @@ int oidnb200_conv_bind(oidnb200_conv* conv, const void* src1, const void* src2, 
                        const void* bias, void* dst)
 {
   const int rc = plan_bind(conv->plan, src1, src2, weights, bias, dst);
-  if (rc == 0 && conv->fused_plan) return plan_bind(*conv->fused_plan, src1, src2, weights, bias, dst);
+  auto embed = [&](ConvPlan& pl) {
+    pl.kp.bias_in_params = 0;
+    if (!getenv("OIDN_B200_SMEM_BIAS") && (int)conv->host_bias.size() == pl.CoutAlloc && pl.CoutAlloc <= kMaxBiasParams)
+    {
+      memcpy(pl.kp.bias_c, conv->host_bias.data(), conv->host_bias.size() * sizeof(float));
+      pl.kp.bias_in_params = 1;
+    }
+  };
+  if (rc == 0) embed(conv->plan);
+  if (rc == 0 && conv->fused_plan)
+  {
+    const int rc2 = plan_bind(*conv->fused_plan, src1, src2, weights, bias, dst);
+    if (rc2 == 0) embed(*conv->fused_plan);
+    return rc2;
+  }
   return rc;
 }
 

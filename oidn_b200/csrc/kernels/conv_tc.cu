@@ -141,6 +141,19 @@ __device__ __forceinline__ void bias_cvt(const uint32_t (&v)[W], const float2* b
   }
 }
 
+// The same with the bias read from the kernel parameters (constant bank; p.bias_in_params): `c` = first channel.
+template <int W>
+__device__ __forceinline__ void bias_cvt_c(const uint32_t (&v)[W], const ConvKernelParams& p, int c, bool relu, uint32_t (&h)[W / 2])
+{
+#pragma unroll
+  for (int i = 0; i < W / 2; ++i)
+  {
+    const float2 s = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                make_float2(p.bias_c[c + 2 * i], p.bias_c[c + 2 * i + 1]));
+    h[i] = relu ? pack_half2_relu(s.x, s.y) : pack_half2(s.x, s.y);
+  }
+}
+
 // Two warpgroups of 128 threads = the 128 TMEM lanes (pixels) of an accumulator. With two streams,
 // warpgroup g drains every row of stream g; with one stream the two warpgroups drain alternate
 // rows (row pairs when pooling). Every WARP is its own store pipeline: it owns the 32 pixels of its
@@ -169,6 +182,7 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
   const int q    = warp & 3;                  // TMEM lane quarter this warp may access
   const bool relu = p.relu != 0;
   const bool direct = p.direct_store != 0;   // registers -> global memory, no staging / TMA store
+  const bool cbias = p.bias_in_params != 0;  // bias from the constant bank instead of shared memory
   const int nbuf = p.out_nbuf;
   const uint32_t wregion = ec.b_region + p.b_bytes + (uint32_t)((wg * 4 + q) * nbuf) * p.out_buf_bytes;
   const int gch0 = ec.group * CoutG;           // first output channel of this CTA's group
@@ -264,7 +278,8 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
             else
               tmem_ld_wait();
             TRACE_END(8);
-            bias_cvt<32>(v, kBiasRegs ? &breg[(c0 + j) / 2] : bias_s + (c0 + j) / 2, relu, h);
+            if (!kBiasRegs && cbias) bias_cvt_c<32>(v, p, gch0 + c0 + j, relu, h);
+            else bias_cvt<32>(v, kBiasRegs ? &breg[(c0 + j) / 2] : bias_s + (c0 + j) / 2, relu, h);
             if (POOL)
             {
 #pragma unroll
@@ -302,7 +317,8 @@ __device__ __forceinline__ void epilogue(const ConvKernelParams& p, const EpiCtx
             else
               tmem_ld_wait();
             TRACE_END(8);
-            bias_cvt<16>(v, kBiasRegs ? &breg[(c0 + j) / 2] : bias_s + (c0 + j) / 2, relu, h);
+            if (!kBiasRegs && cbias) bias_cvt_c<16>(v, p, gch0 + c0 + j, relu, h);
+            else bias_cvt<16>(v, kBiasRegs ? &breg[(c0 + j) / 2] : bias_s + (c0 + j) / 2, relu, h);
             if (POOL)
             {
 #pragma unroll
