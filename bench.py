@@ -267,9 +267,6 @@ def main():
     t1 = time.time()
     ms = e0.elapsed_time(e1) / K
     clocks = sampler.window(t0, t1)
-    # autoexposure (bins + fold) + per tile: input process, convs, output process (separate pass only
-    # when it is not folded into dec_conv0's epilogue; fixed up below from the per-op profile)
-    launches = K * (2 + ntiles * info["numOps"])
 
     # ---- where the frame's time goes -------------------------------------------------------------------------
     # (1) in-frame conv intervals: every conv grid stamps %globaltimer when its first CTA gets past the wait for the
@@ -311,8 +308,11 @@ def main():
     dev.set("profile", 0)
     in_ms = sum(m for _, kind, _, m in prof if kind == 1) / K
     out_ms = sum(m for _, kind, _, m in prof if kind == 2) / K
+    in_launches = sum(n for _, kind, n, _ in prof if kind == 1) // K
     out_launches = sum(n for _, kind, n, _ in prof if kind == 2) // K
-    launches -= K * (ntiles - out_launches)
+    # per frame: autoexposure bins + fold, then per tile the input process, the conv launches (a fused conv pair is
+    # one launch; counted from the kernels' own in-frame stamps) and the output process when it is a pass of its own
+    launches = K * (2 + in_launches + conv_launches + out_launches)
     flop = weights.flops_per_pixel("base", 9) * W * H
     conv_tf = flop / (conv_union_ms * 1e-3) / 1e12
     share = min(conv_union_ms / ms, 1.0)

@@ -20,6 +20,10 @@
 //   * PostOp::Upsample is accepted (isConvSupported), the producer stores its result at its own resolution at the
 //     start of the (4x larger) tensor the core allocated and marks the tensor; a consumer that finds its source
 //     marked reads it through the stride-0 "dup" TMA axis (virtual nearest upsample: no upsampled tensor in HBM);
+//   * a plain conv whose tensor has exactly one reader, another plain conv, runs fused with it as ONE launch
+//     (oidnb200_conv_pair_*: enc_conv0 -> enc_conv1, dec_conv1b -> dec_conv0): the first conv skips its launch, the
+//     second launches the pair -- unless the core's arena planner has put the pair's destination on top of its
+//     source (it may: under two launches the source is dead by then), in which case the two convs run one by one;
 //   * the OutputProcess op finds the conv that produces its source tensor and, when the frame's output image is
 //     packed fp32 RGB, hands it its tile / image / transfer function at submit time: the conv's epilogue writes
 //     the image (oidnb200_conv_set_output_process) and the op's own kernel is skipped (core/unet_filter.cpp:228-236
@@ -122,6 +126,8 @@ OIDN_NAMESPACE_BEGIN
     std::unordered_map<const Tensor*, class B200Conv*> convByDst;
     std::unordered_map<const Tensor*, class B200Conv*> producerOf;   // every conv, by its destination tensor
     std::unordered_map<const Tensor*, int> halfRes;                  // tensors stored at half resolution (virtual upsample)
+    std::unordered_map<const Tensor*, int> readers;                  // how many ops read a tensor (conv pairs need exactly one)
+    std::unordered_map<const Tensor*, class B200Conv*> convReader;   // the last conv that registered as reader of a tensor
   #else
     Ref<Conv> newConv(const ConvDesc&) override { unsupported(); return nullptr; }
     Ref<Pool> newPool(const PoolDesc&) override { unsupported(); return nullptr; }
@@ -524,6 +530,7 @@ OIDN_NAMESPACE_BEGIN
       release();
       detachOutputProcess();
     }
+    friend class B200OutputProcess;
 
     // set by the OutputProcess that consumes this conv's tensor (B200OutputProcess::finalize)
     B200OutputProcess* outputProcess = nullptr;
@@ -547,6 +554,10 @@ OIDN_NAMESPACE_BEGIN
       if (postOp == PostOp::Upsample)
         engine->halfRes[registeredDst] = 1;
       srcHalfRes = engine->halfRes.count(src.get()) != 0;
+      registeredSrc = src.get();
+      engine->readers[registeredSrc] += 1;
+      engine->convReader[registeredSrc] = this;
+      pairChecked = false;
       if (accumulate)
       {
         auto it = engine->convByDst.find(bias.get());
@@ -580,10 +591,53 @@ OIDN_NAMESPACE_BEGIN
       if (postOp == PostOp::Upsample)
         engine->halfRes.erase(registeredDst);
       registeredDst = nullptr;
+      if (registeredSrc)
+      {
+        auto it = engine->readers.find(registeredSrc);
+        if (it != engine->readers.end() && --it->second <= 0)
+          engine->readers.erase(it);
+        auto cr = engine->convReader.find(registeredSrc);
+        if (cr != engine->convReader.end() && cr->second == this)
+          engine->convReader.erase(cr);
+        registeredSrc = nullptr;
+      }
+      dropPair();
+    }
+
+    // conv pair (this = first conv A): `pair` runs A and `pairB` in one launch
+    void dropPair()
+    {
+      if (pair) { oidnb200_conv_pair_destroy(pair); pair = nullptr; }
+      if (pairB) { pairB->pairA = nullptr; pairB = nullptr; }
+      if (pairA) { pairA->dropPair(); }
+    }
+
+    bool isPlain() const { return !accumulate && !absorbed && !partner; }
+
+    void tryPair()
+    {
+      pairChecked = true;
+      if (!isPlain() || postOp != PostOp::None || !dst)
+        return;
+      auto rd = engine->readers.find(dst.get());
+      auto cr = engine->convReader.find(dst.get());
+      if (rd == engine->readers.end() || rd->second != 1 || cr == engine->convReader.end())
+        return;
+      B200Conv* b = cr->second;
+      if (b == this || !b->isPlain() || b->src.get() != dst.get() || b->pairA)
+        return;
+      prepare(); bind();
+      b->prepare(); b->bind();
+      oidnb200_conv_pair* h = nullptr;
+      if (oidnb200_conv_pair_create(handle, b->handle, &h) != 0)
+        return; // shapes not covered: two launches
+      pair = h; pairB = b; b->pairA = this;
     }
 
     void release()
     {
+      dropPair();       // the pair refers to the two kernel-level ops
+      pairChecked = false;
       if (handle) { oidnb200_conv_destroy(handle); handle = nullptr; }
       if (packedWeight) { cudaFree(packedWeight); packedWeight = nullptr; }
       if (packedBias) { cudaFree(packedBias); packedBias = nullptr; }
@@ -654,6 +708,11 @@ OIDN_NAMESPACE_BEGIN
 
     B200Engine* engine;
     const Tensor* registeredDst = nullptr;
+    const Tensor* registeredSrc = nullptr;
+    bool pairChecked = false;
+    oidnb200_conv_pair* pair = nullptr;   // this conv is the first of a fused pair
+    B200Conv* pairB = nullptr;            // ... whose second conv launches it
+    B200Conv* pairA = nullptr;            // this conv is the second of a fused pair
     bool srcHalfRes = false;   // the source tensor holds a half-resolution image (its producer had PostOp::Upsample)
     bool accumulate = false;
     bool absorbed = false;
@@ -732,11 +791,26 @@ OIDN_NAMESPACE_BEGIN
     {
       if (producer)
         producer->outputProcess = nullptr;
+      if (countedSrc)
+      {
+        auto itc = engine->readers.find(countedSrc);
+        if (itc != engine->readers.end() && --itc->second <= 0)
+          engine->readers.erase(itc);
+      }
     }
     Engine* getEngine() const override { return engine; }
 
     void finalize() override
     {
+      if (countedSrc)
+      {
+        auto itc = engine->readers.find(countedSrc);
+        if (itc != engine->readers.end() && --itc->second <= 0)
+          engine->readers.erase(itc);
+      }
+      countedSrc = src ? src.get() : nullptr;
+      if (countedSrc)
+        engine->readers[countedSrc] += 1;
       if (producer)
         producer->outputProcess = nullptr;
       producer = nullptr;
@@ -790,6 +864,7 @@ OIDN_NAMESPACE_BEGIN
   private:
     B200Engine* engine;
     B200Conv* producer = nullptr;
+    const Tensor* countedSrc = nullptr;
     bool fusedThisSubmit = false;
   };
 
@@ -804,10 +879,30 @@ OIDN_NAMESPACE_BEGIN
   {
     if (absorbed)
       return;
+    if (!pairChecked)
+      tryPair();       // every op of the graph has been finalized by the first submit
+    if (pair)
+      return;          // the second conv of the pair launches both
     prepare();
     bind();
-    if (outputProcess)
-      outputProcess->fuseInto(handle);
+    const bool fusedOut = outputProcess && outputProcess->fuseInto(handle);
+    if (pairA)
+    {
+      B200Conv* a = pairA;
+      a->prepare(); a->bind();
+      // The core's arena may alias this conv's destination with the first conv's source (dead by now under two
+      // launches, still being read under one): then run them one by one. With the output process in the epilogue
+      // the destination tensor is not written at all.
+      const char* s0 = static_cast<const char*>(a->src->getPtr()); const char* s1 = s0 + a->src->getByteSize();
+      const char* d0 = static_cast<const char*>(dst->getPtr());    const char* d1 = d0 + dst->getByteSize();
+      if (fusedOut || d1 <= s0 || s1 <= d0)
+      {
+        checkKernel(oidnb200_conv_pair_bind(a->pair), "conv pair bind");
+        checkKernel(oidnb200_conv_pair_launch(a->pair, engine->getStream()), "conv pair");
+        return;
+      }
+      checkKernel(oidnb200_conv_launch(a->handle, engine->getStream()), "conv");
+    }
     checkKernel(oidnb200_conv_launch(handle, engine->getStream()), "conv");
   }
 

@@ -569,7 +569,9 @@ def bench_main(args, rank, world, local_rank):
       "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "frame_on_rank0": on_rank0,
       "tile_plan_alternative": plan_alt, "large_unet_8k": large, "single_process_device": single,
       # all ranks: per tile the filter's ops + one autoexposure-bins launch, per rank one reduce
-      "gpu_launches": K * (ntiles * (info["numOps"] + 1) + world), "clocks": clocks,
+      # all ranks, per tile: autoexposure bins + input process + the conv launches (a fused pair is one; the output
+      # process runs in the last pair's epilogue); per rank one fold of the bin array
+      "gpu_launches": K * (ntiles * (2 + conv_launches // max(ntiles // world, 1)) + world), "clocks": clocks,
       "exchange": "every rank holds its tiles' inputs (tile + overlap); autoexposure: per-tile bin kernels + NCCL all-reduce of the "
                   "bin array (%d B) + fixed-order fold on every rank; output rectangles assembled in rank 0's buffer by copy-engine "
                   "peer writes over NVLink (CUDA IPC); 4-byte all-reduce joins the frame; two frames in flight" % (4 * nbins),

@@ -118,6 +118,15 @@ def run_config(cid, cfg, args, torch):
     res["conv_ms"] = round(conv_ms, 4)
     res["conv_tflops"] = round(weights.flops_per_pixel(kind, ic) * W * H / (conv_ms * 1e-3) / 1e12, 1)
     res["elementwise_ms"] = round(sum(m for _, kind_, _, m in prof if kind_ != 0) / n, 4)
+    # in-frame conv intervals (%globaltimer stamps, frames one at a time): what the frame really spends in convs
+    dev.set("profile", 2)
+    f.execute(); f.profile()
+    for _ in range(n):
+      f.execute()
+    prof2 = f.profile()
+    dev.set("profile", 0)
+    res["conv_union_ms"] = round(sum(m for _, kind_, _, m in prof2 if kind_ == 3) / n, 4)
+    res["conv_layers_in_frame_us"] = {nm: round(m / n * 1e3, 1) for nm, kind_, _, m in prof2 if kind_ == 0 and m > 0}
     got = out.cpu().numpy()
     f.release(); dev.release()
   res["finite"] = bool(np.isfinite(got).all())
