@@ -143,3 +143,48 @@ def test_fused_output_process_argument_checks_without_gpu():
   assert L.oidnb200_last_error()
   for h in (last, wide):
     L.oidnb200_conv_destroy(h)
+
+
+def test_conv_pair_planner_without_gpu():
+  """kernels/conv_pair_tc.cu's planner (host side): which conv -> conv pairs fuse, and with what rings. The TMEM
+  columns of the two accumulator rings, and the shared memory of weights + input ring + mid ring, must fit."""
+  L = capi.lib()
+
+  def conv(H, W, C1, C2, Cout, post=0):
+    d = capi.ConvDesc(H, W, C1, C2, Cout, 1, post, 0, 0)
+    h = C.c_void_p()
+    assert L.oidnb200_conv_create(C.byref(d), C.byref(h)) == 0
+    return h
+
+  def plan(a, b):
+    p = C.c_void_p()
+    rc = L.oidnb200_conv_pair_create(a, b, C.byref(p))
+    if rc != 0:
+      return rc, None
+    i = capi.ConvInfo()
+    assert L.oidnb200_conv_pair_get_info(p, C.byref(i)) == 0
+    L.oidnb200_conv_pair_destroy(p)
+    return 0, {n: getattr(i, n) for n, _ in capi.ConvInfo._fields_}
+
+  H, W = 2160, 3840
+  cases = {  # (C1 of A, Cout of A, Cout of B, pool) -> streams
+    (16, 32, 32, 1): 2,    # base / small: enc_conv0 -> enc_conv1 + pool
+    (64, 32, 16, 0): 2,    # base: dec_conv1b -> dec_conv0
+    (32, 32, 16, 0): 2,    # small: dec_conv1b -> dec_conv0
+    (16, 64, 64, 1): 1,    # large: enc_conv1a -> enc_conv1b + pool (accumulators need all of TMEM)
+    (64, 64, 16, 0): 1,    # large: dec_conv1b -> dec_conv1c (92 KB of resident weights leave room for one stream)
+  }
+  for (c1, ca, cb, pool), streams in cases.items():
+    rc, i = plan(conv(H, W, c1, 0, ca), conv(H, W, ca, 0, cb, pool))
+    assert rc == 0, (c1, ca, cb, pool, L.oidnb200_last_error())
+    # get_info of a pair: ngroups = mid stages, nchunks = A's accumulator slots, ring_slots = B's, nstages = input stages
+    assert i["nstreams"] == streams and i["smem_bytes"] <= 232448 and i["grid"] == 148
+    assert i["nstreams"] * (i["nchunks"] * ca + i["ring_slots"] * cb) <= 512
+    assert i["nchunks"] >= 3 and i["ring_slots"] >= 4 and i["ngroups"] >= 3 and i["nstages"] >= 3
+    assert i["nstrips"] == -(-W // 126) and i["rows_per_item"] % (2 if pool else 1) == 0
+    assert i["nrowchunks"] * i["rows_per_item"] >= H
+  # not fused: concat source, upsampled source, > 64 channels, A with a post-op, different resolution
+  assert plan(conv(H, W, 16, 0, 32), conv(H, W, 32, 16, 32))[0] == -2
+  assert plan(conv(H, W, 96, 0, 96), conv(H, W, 96, 0, 96))[0] == -2
+  assert plan(conv(H, W, 16, 0, 32, 1), conv(H // 2, W // 2, 32, 0, 32))[0] == -2
+  assert plan(conv(H, W, 16, 0, 32), conv(H // 2, W // 2, 32, 0, 32))[0] == -2
