@@ -347,6 +347,29 @@ def single_process_device(args, torch, world, tza, host, K, Wm):
                               "how": "frames one after another (each joins the caller's stream): NVLink stage-in + network + stage-out "
                                      "per frame, CUDA events on engine 0's stream"}
   f.release(); dev.release()
+  # (a') the same frame with the engines on their own streams: back-to-back frames pipeline inside the library
+  #      (stage-in of frame f+1 / stage-out of frame f-1 under the convolutions of frame f). The frames end on internal
+  #      copy-out streams, so this one is the wall clock around K frames between two oidnb200SyncDevice calls.
+  dev = api.Device(tuple(range(world))).commit()
+  f = dev.new_filter("RT")
+  for k, v in t.items():
+    f.set_image(k, v)
+  f.set_image("output", out)
+  f.set("hdr", True); f.set("quality", api.QUALITY_HIGH); f.set_data("weights", tza)
+  f.commit()
+  for _ in range(Wm):
+    f.execute_async()
+  dev.sync()
+  t0 = time.perf_counter()
+  for _ in range(K):
+    f.execute_async()
+  t_enq = time.perf_counter() - t0
+  dev.sync()
+  msp = (time.perf_counter() - t0) / K * 1e3
+  res["frame_in_gpu0_hbm_pipelined"] = {"ms_per_step": round(msp, 4), "value": round(W * H / msp / 1e3, 1), "unit": "Mpix/s",
+                                        "host_enqueue_ms_per_frame": round(t_enq / K * 1e3, 4),
+                                        "how": "engines on their own streams, K frames enqueued back to back, wall clock between two device syncs"}
+  f.release(); dev.release()
   del t, out
   # (b) end to end: the frame lives in pinned host memory; engines on their own streams, frames pipeline in the library
   import bench as B

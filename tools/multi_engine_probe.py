@@ -73,3 +73,37 @@ run("frame in GPU 0 HBM, in place (P2P loads/stores)", 0, "gpu0")
 run("frame in GPU 0 HBM, staged, tilePolicy 2", -1, "gpu0", policy=2)
 run("frame in pinned host memory, staged", -1, "host")
 run("frame in pinned host memory, zero copy", 0, "host")
+
+
+def raw_pcie(n_gpus, mb=512, reps=5):
+  """What the platform gives: concurrent pinned host -> device (and back) copies on n GPUs, aggregate GB/s."""
+  host = [torch.empty(mb << 20, dtype=torch.uint8).pin_memory() for _ in range(n_gpus)]
+  devb, streams = [], []
+  for g in range(n_gpus):
+    with torch.cuda.device(g):
+      devb.append(torch.empty(mb << 20, dtype=torch.uint8, device="cuda"))
+      streams.append(torch.cuda.Stream())
+  res = {}
+  for name, fn in (("H2D", lambda g: devb[g].copy_(host[g], non_blocking=True)), ("D2H", lambda g: host[g].copy_(devb[g], non_blocking=True))):
+    for _ in range(2):
+      for g in range(n_gpus):
+        with torch.cuda.device(g), torch.cuda.stream(streams[g]):
+          fn(g)
+    for g in range(n_gpus):
+      torch.cuda.synchronize(g)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+      for g in range(n_gpus):
+        with torch.cuda.device(g), torch.cuda.stream(streams[g]):
+          fn(g)
+    for g in range(n_gpus):
+      torch.cuda.synchronize(g)
+    res[name] = n_gpus * reps * (mb << 20) / (time.perf_counter() - t0) / 1e9
+  return res
+
+
+for n in sorted({1, 2, min(4, N), N}):
+  if n <= N:
+    r = raw_pcie(n)
+    print("raw pinned-memory copies on %d GPU(s) at once: H2D %.1f GB/s aggregate (%.1f per GPU), D2H %.1f GB/s (%.1f per GPU)"
+          % (n, r["H2D"], r["H2D"] / n, r["D2H"], r["D2H"] / n), flush=True)
