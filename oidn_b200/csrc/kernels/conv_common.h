@@ -90,6 +90,14 @@ struct ConvKernelParams
   int      R;                       // TMEM accumulator ring slots per stream (nstreams*R*CoutG <= 512)
   int      RC, nstrips, nrowchunks; // rows per work item, strips across W, row chunks down H
   int      nstages;                 // A pipeline stages per stream
+  int      up_fold;                 // 1: a virtually upsampled src1 is convolved at ITS OWN row resolution. Upsampled rows
+                                    // 2Y and 2Y+1 are the same low-res row Y, so row Y is staged ONCE (its own ring of
+                                    // nstages_u stages) and used by two consecutive virtual rows with vertically
+                                    // pre-summed weights (conv_plan.cu packs them behind the regular ones): at the even
+                                    // row r = 2Y the usual stack (output rows r+1, r, r-1) takes E = [w0+w1; w1+w2; w2],
+                                    // at the odd row r = 2Y+1 only the fresh row r+1 takes O = [w0]: N = 3+1 row blocks
+                                    // per low-res row instead of 3+3 (two instead of three row taps per output row)
+  int      nstages_u;               // folded: stages [0, nstages_u) of the ring hold src1 chunks, the rest src2 chunks
   int      prefetch_rows;           // > 0: the TMA producer prefetches input rows this far ahead into L2
   uint32_t stage_bytes;             // bytes of the widest A stage: 132 px x the widest K chunk, 1024-aligned
   uint32_t ring_bytes;              // bytes of one stream's A ring

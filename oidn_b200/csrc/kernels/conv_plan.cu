@@ -109,7 +109,24 @@ static int num_sms()
 
 static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
+static int plan_create_impl(const oidnb200_conv_desc& d, ConvPlan& pl, int want_streams, bool allow_fold);
+
+// Row folding of an upsampled src1 (ConvKernelParams::up_fold) pays when the larger resident weights (4 stacked rows
+// per tap instead of 3) neither shrink the output-channel group, nor cost the second stream, nor leave the input rings
+// shallow: plan both ways and keep the folded plan only then (dec_conv1a of the three nets).
 static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_streams = 0 /* 0 = the planner's rule */)
+{
+  const int rc = plan_create_impl(d, pl, want_streams, false);
+  if (rc || !d.src1_upsampled || getenv("OIDN_B200_NO_UPFOLD")) return rc;
+  ConvPlan folded;
+  if (plan_create_impl(d, folded, want_streams, true) == 0 && folded.kp.up_fold &&
+      (getenv("OIDN_B200_FORCE_UPFOLD") ||
+       (folded.kp.CoutG == pl.kp.CoutG && folded.kp.nstreams == pl.kp.nstreams)))
+    pl = folded;
+  return 0;
+}
+
+static int plan_create_impl(const oidnb200_conv_desc& d, ConvPlan& pl, int want_streams, bool allow_fold)
 {
   if (d.H <= 0 || d.W <= 0 || d.C1 <= 0 || d.C1 % 16 || d.C2 < 0 || d.C2 % 16 || d.Cout <= 0 || d.Cout % 16)
   {
@@ -172,10 +189,11 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_strea
   kp.stage_bytes = stage_bytes;
   const int min_stages = 2;
   const uint32_t avail = kSmemBudget - 1024 /*alignment slack*/ - kSmemHeader;
+  const bool fold = d.src1_upsampled && allow_fold;   // ConvKernelParams::up_fold
   auto b_bytes = [&](int CoutG) {
     uint32_t off = 0;
     for (int c = 0; c < n; ++c)
-      off = align_up(off, 1024) + 3u * (3u * CoutG * kp.chunk_cc[c] * 2u);
+      off = align_up(off, 1024) + 3u * ((fold && kp.chunk_up[c] ? 4u : 3u) * CoutG * kp.chunk_cc[c] * 2u);
     return align_up(off, 1024);
   };
   // Output staging: every epilogue warp (2 warpgroups x 4) owns a slice for its 32 pixels (16 after
@@ -211,7 +229,7 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_strea
   {
     off = align_up(off, 1024);
     kp.chunk_boff[c] = off;
-    kp.chunk_bblk[c] = 3u * CoutG * kp.chunk_cc[c] * 2u;
+    kp.chunk_bblk[c] = (fold && kp.chunk_up[c] ? 4u : 3u) * CoutG * kp.chunk_cc[c] * 2u;
     {
       const uint32_t rowb = (uint32_t)kp.chunk_cc[c] * 2u;   // bytes of one staged pixel / weight row
       const uint32_t layout = rowb == 128 ? 2u : (rowb == 64 ? 4u : 6u); // 128B / 64B / 32B swizzle
@@ -226,7 +244,9 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_strea
   }
   const uint32_t bbytes = align_up(off, 1024);
   kp.b_bytes = bbytes;
-  kp.w_bytes = 9u * CoutG * pl.CinTot * 2u;
+  kp.w_bytes = 0;
+  for (int c = 0; c < n; ++c) kp.w_bytes += 3u * kp.chunk_bblk[c];
+  kp.up_fold = fold ? 1 : 0;
 
   // output pieces (same constexpr decomposition the kernel's epilogue is specialised on)
   const int NB = CoutG / 16;
@@ -250,7 +270,30 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_strea
     chunk_stage[c] = align_up(132u * kp.chunk_cc[c] * 2u, 1024);
     row_bytes += chunk_stage[c];
   }
+  // folded: two rings in one table -- U stages (src1 chunks: one set per LOW-RES row) then S stages (src2 chunks: one
+  // set per row); sized for the same look-ahead in rows: NU = n_up * k, NS2 = n_s2 * 2k, plus what still fits
+  int n_up = 0, n_s2 = 0;
+  uint32_t su = 1024, ss = 1024;
+  for (int c = 0; c < n; ++c)
+  {
+    if (kp.chunk_up[c]) { ++n_up; su = std::max(su, chunk_stage[c]); }
+    else { ++n_s2; ss = std::max(ss, chunk_stage[c]); }
+  }
+  int fold_nu = 0, fold_ns = 0;
   auto ring = [&](uint32_t left, int& nstages, bool& by_row) { // one stream's ring inside `left` bytes
+    if (fold)
+    {
+      by_row = false; nstages = 0; fold_nu = fold_ns = 0;
+      int k = 0;
+      while ((uint32_t)((k + 1) * (n_up * su + 2 * n_s2 * ss)) <= left && (k + 1) * (n_up + 2 * n_s2) <= kMaxStages) ++k;
+      if (k < 1) return;
+      fold_nu = n_up * k; fold_ns = 2 * n_s2 * k;
+      uint32_t used = (uint32_t)fold_nu * su + (uint32_t)fold_ns * ss;
+      while (n_s2 && used + ss <= left && fold_nu + fold_ns < kMaxStages) { ++fold_ns; used += ss; }
+      while (used + su <= left && fold_nu + fold_ns < kMaxStages) { ++fold_nu; used += su; }
+      nstages = fold_nu + fold_ns;
+      return;
+    }
     const int uni = std::min((int)(left / stage_bytes), kMaxStages);
     const int rows = std::min((int)(left / row_bytes), kMaxStages / n);
     by_row = rows * n > uni;
@@ -286,7 +329,7 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_strea
       if (fixed + (uint32_t)ns * 2u * stage_bytes > avail) continue;
       int nst; bool br;
       ring(((avail - fixed) / ns) & ~1023u, nst, br);
-      const int want = nbuf == 2 ? 3 : 2;
+      const int want = fold ? 2 * n_up + 2 * n_s2 : (nbuf == 2 ? 3 : 2);   // folded: two low-res rows + two rows in flight
       if (nst < want) continue;
       kp.nstreams = ns; kp.nstages = nst; kp.out_nbuf = nbuf; by_row = br; found = true;
     }
@@ -303,16 +346,17 @@ static int plan_create(const oidnb200_conv_desc& d, ConvPlan& pl, int want_strea
     for (int s2 = 0; s2 < kp.nstages; ++s2)
     {
       kp.stage_off[s2] = off;
-      off += by_row ? chunk_stage[s2 % n] : stage_bytes;
+      off += fold ? (s2 < fold_nu ? su : ss) : (by_row ? chunk_stage[s2 % n] : stage_bytes);
     }
     kp.ring_bytes = off;
+    kp.nstages_u = fold ? fold_nu : 0;
   }
   kp.R = std::min(kMaxSlots, (kTmemCols / kp.nstreams) / CoutG);
   // A ring that cannot hold even one input row (all K chunks) does not hide HBM latency: the TMA
   // producer then pulls the rows ahead into L2 first. Measured (profiles/r01_prefetch_ab.log):
   // dec_conv2a 0.272 -> 0.250 ms, dec_conv3a 0.144 -> 0.139 ms; deeper rings lose ~1 %.
   // OIDN_B200_PREFETCH overrides the choice (hardware probing only).
-  kp.prefetch_rows = (kp.nstages < n) ? 2 : 0;
+  kp.prefetch_rows = (kp.nstages < n && !fold) ? 2 : 0;
   if (const char* e = getenv("OIDN_B200_PREFETCH")) kp.prefetch_rows = atoi(e);
   pl.smem = 1024 + kSmemHeader + (size_t)kp.nstreams * kp.ring_bytes + bbytes +
             (size_t)epi_warps * kp.out_nbuf * kp.out_buf_bytes;
@@ -379,11 +423,23 @@ static int plan_bind(ConvPlan& pl, const void* src1, const void* src2, const voi
       rc = encode_tmap(&kp.amap[c], base, 3, dims, str, box, cc);
     }
     if (rc) return rc;
-    const uint64_t wd[4] = {(uint64_t)pl.CinTot, (uint64_t)pl.CoutAlloc, 3, 3};
-    const uint64_t ws[3] = {(uint64_t)pl.CinTot * 2, (uint64_t)pl.CoutAlloc * pl.CinTot * 2,
-                            (uint64_t)3 * pl.CoutAlloc * pl.CinTot * 2};
-    const uint32_t wb[4] = {(uint32_t)cc, (uint32_t)kp.CoutG, 3, 1};
-    rc = encode_tmap(&kp.wmap[c], weights, 4, wd, ws, wb, cc);
+    if (kp.up_fold && kp.chunk_up[c])
+    {
+      // the folded weights of src1 follow the regular ones: [kw][E0, E1, E2, O][CoutAlloc][C1]
+      const uint8_t* wf = static_cast<const uint8_t*>(weights) + (size_t)9 * pl.CoutAlloc * pl.CinTot * 2;
+      const uint64_t wd[4] = {(uint64_t)d.C1, (uint64_t)pl.CoutAlloc, 4, 3};
+      const uint64_t ws[3] = {(uint64_t)d.C1 * 2, (uint64_t)pl.CoutAlloc * d.C1 * 2, (uint64_t)4 * pl.CoutAlloc * d.C1 * 2};
+      const uint32_t wb[4] = {(uint32_t)cc, (uint32_t)kp.CoutG, 4, 1};
+      rc = encode_tmap(&kp.wmap[c], wf, 4, wd, ws, wb, cc);
+    }
+    else
+    {
+      const uint64_t wd[4] = {(uint64_t)pl.CinTot, (uint64_t)pl.CoutAlloc, 3, 3};
+      const uint64_t ws[3] = {(uint64_t)pl.CinTot * 2, (uint64_t)pl.CoutAlloc * pl.CinTot * 2,
+                              (uint64_t)3 * pl.CoutAlloc * pl.CinTot * 2};
+      const uint32_t wb[4] = {(uint32_t)cc, (uint32_t)kp.CoutG, 3, 1};
+      rc = encode_tmap(&kp.wmap[c], weights, 4, wd, ws, wb, cc);
+    }
     if (rc) return rc;
   }
   {
@@ -679,7 +735,10 @@ void oidnb200_conv_destroy(oidnb200_conv* conv) { delete conv; }
 
 size_t oidnb200_conv_weight_bytes(const oidnb200_conv* conv)
 {
-  return (size_t)9 * conv->plan.CoutAlloc * conv->plan.CinTot * sizeof(uint16_t);
+  const ConvPlan& pl = conv->plan;
+  size_t n = (size_t)9 * pl.CoutAlloc * pl.CinTot;
+  if (pl.kp.up_fold) n += (size_t)12 * pl.CoutAlloc * pl.desc.C1;   // [kw][4][CoutAlloc][C1]: vertically pre-summed src1 weights
+  return n * sizeof(uint16_t);
 }
 
 size_t oidnb200_conv_bias_bytes(const oidnb200_conv* conv)
@@ -708,6 +767,24 @@ int oidnb200_conv_pack_weights(const oidnb200_conv* conv, const uint16_t* w_oihw
           dst[((size_t)(kw * 3 + kh) * pl.CoutAlloc + o) * pl.CinTot + ci] =
             w_oihw[(((size_t)o * I + i) * 3 + kh) * 3 + kw];
     }
+  if (pl.kp.up_fold)
+  {
+    // Row folding of the upsampled src1: upsampled rows 2Y and 2Y+1 are both low-res row Y. At the even virtual row
+    // r = 2Y the stack (output rows r+1, r, r-1) takes E = [w0+w1; w1+w2; w2] (kh taps that land on row Y), at the odd
+    // row r = 2Y+1 the fresh output row r+1 takes O = [w0]. Sums in fp32, rounded to fp16 once.
+    uint16_t* f = dst + (size_t)9 * pl.CoutAlloc * pl.CinTot;
+    const int C1 = pl.desc.C1;
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I1; ++i)
+        for (int kw = 0; kw < 3; ++kw)
+        {
+          float w[3];
+          for (int kh = 0; kh < 3; ++kh) w[kh] = half_bits_to_float(w_oihw[(((size_t)o * I + i) * 3 + kh) * 3 + kw]);
+          const float st[4] = {w[0] + w[1], w[1] + w[2], w[2], w[0]};
+          for (int j = 0; j < 4; ++j)
+            f[((size_t)(kw * 4 + j) * pl.CoutAlloc + o) * C1 + i] = float_to_half_bits(st[j]);
+        }
+  }
   return 0;
 }
 

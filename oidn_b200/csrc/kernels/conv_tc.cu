@@ -551,7 +551,9 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
         pdl_wait();
         // in-frame start stamp: the prerequisite grid has completed, this grid's first activation load follows
         if (p.stamps && st == 0 && leader) atomicMin(&p.stamps[0], globaltimer_ns());
-        uint32_t s = 0, ph = 0;
+        uint32_t s = 0, ph = 0;            // cursor of the ring (of its src2 part when folded)
+        uint32_t su = 0, phu = 0;          // folded: cursor of the src1 part (stages [0, NU))
+        const uint32_t NU = (uint32_t)p.nstages_u, NS2 = (uint32_t)NS - NU;
         const int PF = p.prefetch_rows;
         for (int item = vcta; item < nitems; item += nv)
         {
@@ -580,9 +582,14 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
             }
             for (int c = 0; c < p.nchunks; ++c)
             {
-              const uint32_t full = full_a + 8 * s;
-              const uint32_t dst  = a_ring + p.stage_off[s];
-              MBAR_WAIT(empty_a + 8 * s, ph ^ 1, 1);
+              // row folding: an upsampled source is staged once per LOW-RES row (virtual rows 2Y and 2Y+1 are the same
+              // data): at even rows, and at the item's first row whatever its parity
+              const bool useU = p.up_fold && p.chunk_up[c];
+              if (useU && (r & 1) && r != it.y0 - 1) continue;
+              const uint32_t bi = useU ? su : NU + s;
+              const uint32_t full = full_a + 8 * bi;
+              const uint32_t dst  = a_ring + p.stage_off[bi];
+              MBAR_WAIT(empty_a + 8 * bi, (useU ? phu : ph) ^ 1, 1);
               const int cc = p.chunk_cc[c];
               if (leader)
               {
@@ -600,7 +607,8 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
                   tma_load_3d(dst, &p.amap[c], full, p.chunk_c0[c], it.x0 - 1, r);
                 }
               }
-              if (++s == (uint32_t)NS) { s = 0; ph ^= 1; }
+              if (useU) { if (++su == NU) { su = 0; phu ^= 1; } }
+              else      { if (++s == NS2) { s = 0; ph ^= 1; } }
             }
           }
         }
@@ -625,7 +633,11 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
         const int nchunks = p.nchunks;
         MBAR_WAIT(sbase + SmemLayout::w_full, 0, 2);
         tc_fence_after();
-        uint32_t stage = 0, sphase = 0;       // A ring position / parity
+        uint32_t stage = 0, sphase = 0;       // A ring position / parity (of the ring's src2 part when folded)
+        uint32_t stage_u = 0, sphase_u = 0;   // folded: position / parity of the src1 part (stages [0, NU))
+        uint32_t held_u = 0;                  // folded: first src1 stage of the low-res row staged at the last even row
+        const uint32_t NU = (uint32_t)p.nstages_u, NS2 = (uint32_t)NS - NU;
+        const bool fold = p.up_fold != 0;
         uint32_t a_mod = 0, a_par = 0;        // (first accumulator index of the item) % R, parity of / R
         for (int item = vcta; item < nitems; item += nv)
         {
@@ -658,47 +670,83 @@ __device__ __forceinline__ void conv3x3_tc_body(const ConvKernelParams& p)
             const uint32_t idesc_r0 = umma_idesc_f16(n0 * CoutG);
             const uint32_t idesc_r1 = umma_idesc_f16(n1 * CoutG);
 
+            uint32_t ui = 0;   // folded: ordinal of the src1 chunk inside this row
             for (int c = 0; c < nchunks; ++c)
             {
               const uint32_t nk     = p.chunk_nk[c];                 // 16-channel k-steps: 1, 2 or 4
               const uint32_t row16  = nk * 2;                        // row bytes / 16
               const uint32_t hi     = p.chunk_hi[c];                 // SBO, version, swizzle
-              const uint32_t a_lo   = ring16 + (p.stage_off[stage] >> 4) + p.chunk_a16[c]; // upsampled rows start at x0-2
+              // Which stage, which weights, which accumulators. Folded src1 chunk (ConvKernelParams::up_fold): the
+              // low-res row is staged at the even row (or the item's first row) and serves the odd row after it too --
+              // there with the O weights (block 3), into the fresh output row r+1 only.
+              uint32_t bi = NU + stage;       // index into the stage table / barrier arrays
+              bool wait_stage = true, release = true, useU = false;
+              uint32_t cn0 = n0, cn1 = n1, crb0 = brow0 * row16, crb1 = brow1 * row16, cd0 = d0, cid0 = idesc_r0;
+              if (fold && p.chunk_up[c])
+              {
+                useU = true;
+                const bool odd = (r & 1) != 0, start = (r == it.y0 - 1);
+                if (odd && !start)
+                {
+                  const uint32_t my = ui++;
+                  if (kh_lo > 0) continue;                      // output row r+1 is outside the item (stage released at the even row)
+                  bi = held_u + my; if (bi >= NU) bi -= NU;
+                  wait_stage = false;
+                }
+                else
+                {
+                  if (ui == 0) held_u = stage_u;
+                  ++ui;
+                  bi = stage_u;
+                  if (!odd && r + 2 <= it.y1) release = false;    // the odd row that follows still needs it
+                }
+                if (odd)
+                {
+                  // kh = 0 only: one row block, the O weights
+                  cn0 = 1; cn1 = 0; crb0 = 3u * CoutG * row16; crb1 = 0;
+                  cd0 = tbase + ((uint32_t)(R - 1) - top_mod) * CoutG; cid0 = idesc1;
+                  if (kh_lo > 0) { if (wait_stage) { /* item start at an odd row always has kh_lo == 0 */ } }
+                }
+              }
+              const uint32_t a_lo   = ring16 + (p.stage_off[bi] >> 4) + p.chunk_a16[c]; // upsampled rows start at x0-2
               const uint32_t b_lo   = breg16 + p.chunk_b16[c];
               const uint32_t bblk16 = p.chunk_bblk16[c];
-              const uint32_t rb0 = brow0 * row16, rb1 = brow1 * row16;
               const bool first = fresh && c == 0;
-              MBAR_WAIT(full_a + 8 * stage, sphase, 4);
-              tc_fence_after();
+              if (wait_stage)
+              {
+                MBAR_WAIT(full_a + 8 * bi, useU ? sphase_u : sphase, 4);
+                tc_fence_after();
+              }
               TRACE_BEGIN();
               if (leader)
               {
                 if (first)
                 {
                   // the first contribution to the fresh accumulator (kh=0 block of run 0) overwrites it
-                  umma_f16(d0, make_desc(hi, a_lo), make_desc(hi, b_lo + rb0), idesc1, 0u);
-                  if (n0 > 1)
-                    umma_f16(d0 + CoutG, make_desc(hi, a_lo), make_desc(hi, b_lo + rb0 + CoutG * row16),
-                             umma_idesc_f16((n0 - 1) * CoutG), 1u);
-                  if (n1)
-                    umma_f16(d1, make_desc(hi, a_lo), make_desc(hi, b_lo + rb1), idesc_r1, 1u);
+                  umma_f16(cd0, make_desc(hi, a_lo), make_desc(hi, b_lo + crb0), idesc1, 0u);
+                  if (cn0 > 1)
+                    umma_f16(cd0 + CoutG, make_desc(hi, a_lo), make_desc(hi, b_lo + crb0 + CoutG * row16),
+                             umma_idesc_f16((cn0 - 1) * CoutG), 1u);
+                  if (cn1)
+                    umma_f16(d1, make_desc(hi, a_lo), make_desc(hi, b_lo + crb1), idesc_r1, 1u);
                 }
-                if (n1)
+                if (cn1)
                 {
-                  if (nk == 4)      issue_chunk<4, true>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else if (nk == 2) issue_chunk<2, true>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else              issue_chunk<1, true>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  if (nk == 4)      issue_chunk<4, true>(hi, a_lo, b_lo, bblk16, cd0, cid0, crb0, d1, idesc_r1, crb1, first);
+                  else if (nk == 2) issue_chunk<2, true>(hi, a_lo, b_lo, bblk16, cd0, cid0, crb0, d1, idesc_r1, crb1, first);
+                  else              issue_chunk<1, true>(hi, a_lo, b_lo, bblk16, cd0, cid0, crb0, d1, idesc_r1, crb1, first);
                 }
                 else
                 {
-                  if (nk == 4)      issue_chunk<4, false>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else if (nk == 2) issue_chunk<2, false>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
-                  else              issue_chunk<1, false>(hi, a_lo, b_lo, bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, first);
+                  if (nk == 4)      issue_chunk<4, false>(hi, a_lo, b_lo, bblk16, cd0, cid0, crb0, d1, idesc_r1, crb1, first);
+                  else if (nk == 2) issue_chunk<2, false>(hi, a_lo, b_lo, bblk16, cd0, cid0, crb0, d1, idesc_r1, crb1, first);
+                  else              issue_chunk<1, false>(hi, a_lo, b_lo, bblk16, cd0, cid0, crb0, d1, idesc_r1, crb1, first);
                 }
-                umma_commit(empty_a + 8 * stage); // stage reusable once these MMAs retire
+                if (release) umma_commit(empty_a + 8 * bi); // stage reusable once these MMAs retire
               }
               TRACE_END(8);
-              if (++stage == (uint32_t)NS) { stage = 0; sphase ^= 1; }
+              if (useU) { if (wait_stage) { if (++stage_u == NU) { stage_u = 0; sphase_u ^= 1; } } }
+              else      { if (++stage == NS2) { stage = 0; sphase ^= 1; } }
             }
             // Output row r-1 has now received kh=0,1,2.
             if (r - 1 >= it.y0 && r - 1 <= it.y1)
