@@ -3,6 +3,8 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
+
 from oidn_b200 import api, capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -188,3 +190,43 @@ def test_conv_pair_planner_without_gpu():
   assert plan(conv(H, W, 96, 0, 96), conv(H, W, 96, 0, 96))[0] == -2
   assert plan(conv(H, W, 16, 0, 32, 1), conv(H // 2, W // 2, 32, 0, 32))[0] == -2
   assert plan(conv(H, W, 16, 0, 32), conv(H // 2, W // 2, 32, 0, 32))[0] == -2
+
+
+def test_row_folding_plan_and_weights_without_gpu(monkeypatch):
+  """ConvKernelParams::up_fold (host side): the planner folds an upsampled source only when it keeps the channel group
+  and both streams (dec_conv1a), and oidnb200_conv_pack_weights appends the vertically pre-summed taps
+  [kw][w0+w1, w1+w2, w2, w0][CoutAlloc][C1] behind the regular [kw][kh][CoutAlloc][CinTot] block."""
+  L = capi.lib()
+
+  def make(H, W, C1, C2, Co, up):
+    d = capi.ConvDesc(H, W, C1, C2, Co, 1, 0, up, 0)
+    h = C.c_void_p()
+    assert L.oidnb200_conv_create(C.byref(d), C.byref(h)) == 0, L.oidnb200_last_error()
+    return h
+
+  regular = lambda C1, C2, Co: 9 * Co * (C1 + C2) * 2
+  # dec_conv1a (64 upsampled + 16 skip -> 64): folded; dec_conv2a (96 + 32 -> 64): the folded weights do not fit -> regular
+  a = make(2160, 3840, 64, 16, 64, 1)
+  assert L.oidnb200_conv_weight_bytes(a) == regular(64, 16, 64) + 12 * 64 * 64 * 2
+  i = capi.ConvInfo(); L.oidnb200_conv_get_info(a, C.byref(i))
+  assert i.nstreams == 2 and i.cout_group == 64 and i.ring_slots == 4 and i.smem_bytes <= 232448
+  assert L.oidnb200_conv_weight_bytes(make(1080, 1920, 96, 32, 64, 1)) == regular(96, 32, 64)
+  assert L.oidnb200_conv_weight_bytes(make(2160, 3840, 64, 16, 64, 0)) == regular(64, 16, 64)      # not upsampled
+  monkeypatch.setenv("OIDN_B200_NO_UPFOLD", "1")
+  assert L.oidnb200_conv_weight_bytes(make(2160, 3840, 64, 16, 64, 1)) == regular(64, 16, 64)
+  monkeypatch.delenv("OIDN_B200_NO_UPFOLD")
+
+  O, I1, I2, C1, C2, Co = 61, 64, 9, 64, 16, 64
+  rng = np.random.default_rng(5)
+  w = (rng.standard_normal((O, I1 + I2, 3, 3)) * 0.1).astype(np.float16)
+  buf = np.zeros(L.oidnb200_conv_weight_bytes(a) // 2, np.float16)
+  assert L.oidnb200_conv_pack_weights(a, w.ctypes.data, O, I1, I2, buf.ctypes.data) == 0
+  reg = buf[:9 * Co * (C1 + C2)].reshape(3, 3, Co, C1 + C2)          # [kw][kh][o][ci]
+  fol = buf[9 * Co * (C1 + C2):].reshape(3, 4, Co, C1)               # [kw][E0,E1,E2,O][o][i]
+  np.testing.assert_array_equal(reg[:, :, :O, :I1], w[:, :I1].transpose(3, 2, 0, 1))
+  np.testing.assert_array_equal(reg[:, :, :O, C1:C1 + I2], w[:, I1:].transpose(3, 2, 0, 1))
+  wf = w[:, :I1].astype(np.float32)                                   # [o][i][kh][kw]
+  stacks = [wf[:, :, 0] + wf[:, :, 1], wf[:, :, 1] + wf[:, :, 2], wf[:, :, 2], wf[:, :, 0]]
+  for j, st in enumerate(stacks):
+    np.testing.assert_array_equal(fol[:, j, :O, :I1], st.astype(np.float16).transpose(2, 0, 1))
+  assert not fol[:, :, O:].any() and not fol[:, :, :, I1:].any()      # padding stays zero
