@@ -1050,7 +1050,9 @@ void UNetFilter::execute(SyncMode sync)
     submitFrame(progress);
   }
 
-  if (profiling)
+  // events (mode 1) are read back per frame; in-frame stamps (mode 2) stay on the device until the profile is asked
+  // for, so that consecutive frames are stamped as they really run, back to back
+  if (profiling == 1)
     for (auto& inst : instances) inst.graph->collectProfile(profile);
 
   if (sync == SyncMode::Blocking || progress)
@@ -1060,7 +1062,12 @@ void UNetFilter::execute(SyncMode sync)
   }
 }
 
-std::vector<Graph::OpTime> UNetFilter::getProfile() { return profile; }
+std::vector<Graph::OpTime> UNetFilter::getProfile()
+{
+  for (auto& inst : instances)
+    if (inst.graph->hasPendingStamps()) inst.graph->collectProfile(profile);
+  return profile;
+}
 
 // ------------------------------------------------------------------------------------------------
 // RTFilter (core/rt_filter.cpp)

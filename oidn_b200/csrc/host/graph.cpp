@@ -234,16 +234,23 @@ void Graph::submit()
     const size_t n = convs.size() * 2;
     if (profiling == 2)
     {
-      if (!stampBuf) stampBuf = engine->malloc(n * sizeof(unsigned long long));
+      if (!stampBuf) stampBuf = engine->malloc((size_t)kStampSlices * n * sizeof(unsigned long long));
+      if (stampSlice == kStampSlices) collectStamps();   // all slices used: read them back (waits for the stream)
       stampHost.assign(n, 0ull);
       for (size_t i = 0; i < convs.size(); ++i) stampHost[2 * i] = ~0ull;
-      checkCuda(cudaMemcpyAsync(stampBuf, stampHost.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+      unsigned long long* slice = static_cast<unsigned long long*>(stampBuf) + (size_t)stampSlice * n;
+      checkCuda(cudaMemcpyAsync(slice, stampHost.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice,
                                 static_cast<cudaStream_t>(engine->getStream())), "cudaMemcpyAsync (stamps)");
+      for (size_t i = 0; i < convs.size(); ++i)
+        oidnb200_conv_set_stamps(convs[i].conv->getHandle(), slice + 2 * i);
+      ++stampSlice;
     }
-    for (size_t i = 0; i < convs.size(); ++i)
-      oidnb200_conv_set_stamps(convs[i].conv->getHandle(),
-                               profiling == 2 ? static_cast<unsigned long long*>(stampBuf) + 2 * i : nullptr);
-    if (profiling != 2) { engine->wait(); engine->free(stampBuf); stampBuf = nullptr; }
+    else
+    {
+      if (stampSlice > 0) collectStamps();
+      for (size_t i = 0; i < convs.size(); ++i) oidnb200_conv_set_stamps(convs[i].conv->getHandle(), nullptr);
+      engine->wait(); engine->free(stampBuf); stampBuf = nullptr;
+    }
   }
   // a fused pair replaces the launches of its two convs: A is skipped, the pair runs in B's place
   auto submitOp = [&](size_t i) {
@@ -262,7 +269,6 @@ void Graph::submit()
       if (!(fused && ops[i] == outputProcess)) submitOp(i);
       if (opCallback) opCallback();
     }
-    if (profiling == 2) collectStamps();
     return;
   }
   cudaStream_t st = static_cast<cudaStream_t>(engine->getStream());
@@ -284,31 +290,39 @@ void Graph::collectStamps()
 {
   engine->wait();
   const size_t n = convs.size();
-  checkCuda(cudaMemcpy(stampHost.data(), stampBuf, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "cudaMemcpy (stamps)");
+  std::vector<unsigned long long> all((size_t)stampSlice * 2 * n);
+  if (!all.empty())
+    checkCuda(cudaMemcpy(all.data(), stampBuf, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "cudaMemcpy (stamps)");
   stampMs.resize(n + 1, 0.); stampLaunches.resize(n + 1, 0);
-  std::vector<std::pair<unsigned long long, unsigned long long>> iv;
-  for (size_t i = 0; i < n; ++i)
+  for (int sl = 0; sl < stampSlice; ++sl)
   {
-    const unsigned long long t0 = stampHost[2 * i], t1 = stampHost[2 * i + 1];
-    if (t1 <= t0) continue; // not launched
-    stampMs[i] += (double)(t1 - t0) * 1e-6;
-    stampLaunches[i] += 1;
-    iv.emplace_back(t0, t1);
+    const unsigned long long* st = all.data() + (size_t)sl * 2 * n;
+    std::vector<std::pair<unsigned long long, unsigned long long>> iv;
+    for (size_t i = 0; i < n; ++i)
+    {
+      const unsigned long long t0 = st[2 * i], t1 = st[2 * i + 1];
+      if (t1 <= t0) continue; // not launched (first conv of a fused pair)
+      stampMs[i] += (double)(t1 - t0) * 1e-6;
+      stampLaunches[i] += 1;
+      iv.emplace_back(t0, t1);
+    }
+    std::sort(iv.begin(), iv.end());
+    unsigned long long total = 0, curEnd = 0;
+    for (const auto& v : iv)
+    {
+      if (v.first >= curEnd) { total += v.second - v.first; curEnd = v.second; }
+      else if (v.second > curEnd) { total += v.second - curEnd; curEnd = v.second; }
+    }
+    stampMs[n] += (double)total * 1e-6;
+    stampLaunches[n] += 1;
   }
-  std::sort(iv.begin(), iv.end());
-  unsigned long long total = 0, curEnd = 0;
-  for (const auto& v : iv)
-  {
-    if (v.first >= curEnd) { total += v.second - v.first; curEnd = v.second; }
-    else if (v.second > curEnd) { total += v.second - curEnd; curEnd = v.second; }
-  }
-  stampMs[n] += (double)total * 1e-6;
-  stampLaunches[n] += 1;
+  stampSlice = 0;
 }
 
 void Graph::collectProfile(std::vector<OpTime>& out)
 {
   engine->wait();
+  if (stampSlice > 0) collectStamps();
   if (!stampMs.empty())
   {
     // in-frame stamp mode: one entry per op (convs filled) + the union entry

@@ -61,6 +61,7 @@ public:
   void setFusePairs(bool on) { fusePairs = on; }
   int getNumPairs() const { return (int)pairs.size(); }
   void collectProfile(std::vector<OpTime>& out);
+  bool hasPendingStamps() const { return stampSlice > 0; }
 
   const std::shared_ptr<InputProcess>& getInputProcess() const { return inputProcess; }
   const std::shared_ptr<OutputProcess>& getOutputProcess() const { return outputProcess; }
@@ -113,7 +114,10 @@ private:
   int profiling = 0;
   struct Stamp { int op; void* e0; void* e1; };
   std::vector<Stamp> stamps;
-  void* stampBuf = nullptr;                       // device: 2 x uint64 per conv
+  void* stampBuf = nullptr;                       // device: kStampSlices x (2 x uint64 per conv): one slice per submit, so
+                                                  // consecutive frames are stamped without a host sync between them
+  static constexpr int kStampSlices = 64;
+  int stampSlice = 0;                             // slices used since the last collect
   std::vector<unsigned long long> stampHost;      // init pattern / read-back
   std::vector<double> stampMs;                    // per conv (accumulated), last entry: union
   std::vector<int> stampLaunches;

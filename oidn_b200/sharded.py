@@ -440,7 +440,7 @@ def bench_main(args, rank, world, local_rank):
       sf.execute_async(); torch.cuda.synchronize(); sf.filter.profile()
       for _ in range(frames):
         sf.execute_async()
-        torch.cuda.synchronize()
+      torch.cuda.synchronize()
       prof = sf.filter.profile()
       dev.set("profile", 0)
     dist.barrier()

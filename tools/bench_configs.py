@@ -122,7 +122,8 @@ def run_config(cid, cfg, args, torch):
     dev.set("profile", 2)
     f.execute(); f.profile()
     for _ in range(n):
-      f.execute()
+      f.execute_async()
+    torch.cuda.synchronize()
     prof2 = f.profile()
     dev.set("profile", 0)
     res["conv_union_ms"] = round(sum(m for _, kind_, _, m in prof2 if kind_ == 3) / n, 4)
