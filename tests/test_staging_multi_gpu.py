@@ -374,3 +374,84 @@ def test_large_unet_clean_aux_multi_tile_vs_oracle(W, H, engines, oracle):
   print("large UNet cleanAux %dx%d, %dx%d tiles, %d engine(s): max|err|/peak = %.3e, PSNR = %.1f dB"
         % (W, H, info["tileCountW"], info["tileCountH"], engines, e, p))
   assert e <= MAX_ERR and p >= MIN_PSNR, (e, p)
+
+
+def test_staged_half_and_row_strided_host_images():
+  """Staging moves row segments with copy engines: half-precision images (6-byte pixels), a row stride wider than the
+  image, and a 1-channel image go through it unchanged; strided PIXELS are not staged (copy engines cannot skip
+  bytes) and fall back to zero copy. Every variant == the same images resident on the device."""
+  W, H = 1700, 420
+  tza = weights.model_tza("base", 3, seed=0)
+  color = synth.benchmark_images(W, H, hdr=False, albedo=False, normal=False, seed=48)["color"]
+  dev = api.Device((0,)).commit()
+  dev.set("maxTilePixels", 1000 * 432)     # two tiles
+
+  def run(cimg, oimg):
+    f = dev.new_filter("RT")
+    f.set_image("color", cimg); f.set_image("output", oimg); f.set_data("weights", tza)
+    f.commit(); f.execute()
+    info = f.info()
+    f.release()
+    return info
+
+  for dtype in (torch.float16, torch.float32):
+    c = torch.from_numpy(color).to(dtype)
+    ref = torch.zeros((H, W, 3), dtype=dtype, device="cuda")
+    assert run(c.cuda(), ref)["staged"] == 0
+    # packed host images
+    hc, ho = c.clone().pin_memory(), torch.zeros((H, W, 3), dtype=dtype).pin_memory()
+    info = run(hc, ho)
+    assert info["staged"] == 1 and info["tileCountH"] * info["tileCountW"] > 1
+    assert torch.equal(ho, ref.cpu())
+    # rows padded to W + 9 pixels
+    big_c = torch.zeros((H, W + 9, 3), dtype=dtype).pin_memory(); big_c[:, 4:4 + W] = c
+    big_o = torch.full((H, W + 9, 3), -5.0, dtype=dtype).pin_memory()
+    assert run(big_c[:, 4:4 + W], big_o[:, 2:2 + W])["staged"] == 1
+    assert torch.equal(big_o[:, 2:2 + W], ref.cpu())
+    assert bool((big_o[:, :2] == -5).all()) and bool((big_o[:, 2 + W:] == -5).all()), "wrote outside the image"
+    # strided pixels (4 values per pixel, 3 used): not staged, dereferenced in place
+    wide_c = torch.zeros((H, W, 4), dtype=dtype).pin_memory(); wide_c[:, :, :3] = c
+    wide_o = torch.zeros((H, W, 4), dtype=dtype).pin_memory()
+    assert run(wide_c[:, :, :3], wide_o[:, :, :3])["staged"] == 0
+    assert torch.equal(wide_o[:, :, :3], ref.cpu()) and not bool(wide_o[:, :, 3].any())
+  # one channel
+  c1 = torch.from_numpy(color[:, :, :1].copy())
+  ref1 = torch.zeros((H, W, 1), device="cuda")
+  run(c1.cuda(), ref1)
+  h1, o1 = c1.clone().pin_memory(), torch.zeros((H, W, 1)).pin_memory()
+  assert run(h1, o1)["staged"] == 1
+  assert torch.equal(o1, ref1.cpu())
+  dev.release()
+
+
+def test_staged_progress_and_cancel():
+  """Progress monitor on a staged frame: one unit per op of every tile (+1 for the autoexposure), reported from the
+  engines' compute streams; returning false cancels with OIDN_ERROR_CANCELLED and leaves the device usable."""
+  W, H = 900, 500
+  tza = weights.model_tza("base", 9, seed=0)
+  frame = synth.benchmark_images(W, H, hdr=True, seed=49)
+  dev = api.Device((0, 0)).commit()
+  host = {k: torch.from_numpy(v).pin_memory() for k, v in frame.items()}
+  hout = torch.zeros((H, W, 3)).pin_memory()
+  f = dev.new_filter("RT")
+  for k, v in host.items():
+    f.set_image(k, v)
+  f.set_image("output", hout); f.set("hdr", True); f.set_data("weights", tza)
+  seen = []
+  f.set_progress_monitor(lambda n: (seen.append(n), True)[1])
+  f.commit(); f.execute()
+  info = f.info()
+  ntiles = info["tileCountH"] * info["tileCountW"]
+  assert info["staged"] == 1 and ntiles % 2 == 0
+  assert seen[0] == 0.0 and seen[-1] == 1.0 and all(b >= a for a, b in zip(seen, seen[1:]))
+  assert len(seen) == 1 + ntiles * info["numOps"] + 1
+  good = hout.clone()
+  f.set_progress_monitor(lambda n: n < 0.3)
+  with pytest.raises(api.Error) as ei:
+    f.execute()
+  assert ei.value.code == capi.ERROR_CANCELLED
+  f.set_progress_monitor(None)
+  hout.zero_()
+  f.execute()
+  assert torch.equal(hout, good)
+  f.release(); dev.release()
