@@ -203,6 +203,17 @@ OIDNB200_API int oidnb200_autoexposure_bins_launch(const oidnb200_image* src, in
 OIDNB200_API int oidnb200_autoexposure_reduce_launch(const float* bins, int num_bins, float* dst,
                                                      oidnb200_stream stream);
 
+/* Peer flags: frame-level hand-shake between the GPUs of a tile-sharded frame without a collective (the role
+ * Device::submitBarrier plays between the engines of one process, core/unet_filter.cpp:178,243, when the engines are
+ * in different processes). A flag array holds one uint32 per rank, in device memory every rank can reach (CUDA IPC /
+ * peer access). signal: stores `value` (a growing frame sequence number) into the n given slots -- this rank's slot
+ * of every rank's array -- after everything enqueued before it on the stream has completed. wait: returns (in stream
+ * order) once all n slots of the LOCAL array hold at least `value`; traps after timeout_s seconds (0 = 10 s) instead
+ * of hanging. Both are one 32-thread block without shared memory: they run next to a persistent conv CTA. */
+OIDNB200_API int oidnb200_flag_signal_launch(void* const* slots, int n, unsigned int value, oidnb200_stream stream);
+OIDNB200_API int oidnb200_flag_wait_launch(const void* flags, int n, unsigned int value, double timeout_s,
+                                           oidnb200_stream stream);
+
 /* ImageCopy (core/image_copy.h, devices/gpu/gpu_image_copy.h:15-27): same format and size. */
 OIDNB200_API int oidnb200_image_copy_launch(const oidnb200_image* src, const oidnb200_image* dst,
                                             oidnb200_stream stream);

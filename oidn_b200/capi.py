@@ -87,6 +87,8 @@ KERNEL_ABI = {
   "oidnb200_autoexposure_bin_grid": (None, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
   "oidnb200_autoexposure_bins_launch": (C.c_int, [C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
   "oidnb200_autoexposure_reduce_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+  "oidnb200_flag_signal_launch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_void_p]),
+  "oidnb200_flag_wait_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.c_double, C.c_void_p]),
   "oidnb200_image_copy_launch": (C.c_int, [C.POINTER(Image), C.POINTER(Image), C.c_void_p]),
   "oidnb200_pool_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
   "oidnb200_upsample_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

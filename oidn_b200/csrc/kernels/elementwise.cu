@@ -487,6 +487,55 @@ __global__ void __launch_bounds__(256) upsample_kernel(const uint4* __restrict__
   dst[idx] = src[((size_t)(y >> 1) * W + (x >> 1)) * C8 + c];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Peer flags: the frame-level hand-shake of tile-sharded execution over several processes / GPUs without a
+// collective. A rank that has finished a step (its autoexposure bins are in every peer's bin array; its output
+// rectangles are in the frame) stores the frame's sequence number into its slot of every rank's flag array -- peer
+// stores over NVLink from one tiny block -- and a rank that needs the step waits until every slot of its OWN array has
+// reached the number. Both kernels are one block without shared memory: they co-reside with a persistent conv CTA
+// (which a collective's kernel, with its shared memory, cannot), so the other frame in flight keeps every SM.
+// ------------------------------------------------------------------------------------------------
+struct FlagTargets
+{
+  unsigned int* slot[16];   // this rank's slot in every rank's flag array (own array included)
+  int n;
+};
+
+__global__ void __launch_bounds__(32) flag_signal_kernel(const FlagTargets t, unsigned int value)
+{
+  // stream order has completed this rank's copies; make them visible system-wide before the flag
+  __threadfence_system();
+  if ((int)threadIdx.x < t.n)
+  {
+    volatile unsigned int* d = t.slot[threadIdx.x];
+    *d = value;
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(32) flag_wait_kernel(const unsigned int* flags, int n, unsigned int value, unsigned long long timeout_ns)
+{
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if ((int)threadIdx.x < n)
+  {
+    const volatile unsigned int* f = flags + threadIdx.x;
+    // sequence numbers only grow; compare as a signed difference so a 32-bit wrap does not stall
+    while ((int)(*f - value) < 0)
+    {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns)
+      {
+        printf("[oidn_b200] peer flag timeout: slot %d holds %u, waiting for %u\n", (int)threadIdx.x, *f, value);
+        __trap();
+      }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
 int check_launch(const char* what)
 {
   const cudaError_t e = cudaGetLastError();
@@ -657,6 +706,32 @@ int oidnb200_image_copy_launch(const oidnb200_image* src, const oidnb200_image* 
   dim3 grid((d.W + threads - 1) / threads, d.H);
   image_copy_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(s, d, s.C * (s.is_half ? 2 : 4));
   return check_launch("image_copy");
+}
+
+int oidnb200_flag_signal_launch(void* const* slots, int n, unsigned int value, oidnb200_stream stream)
+{
+  if (!slots || n < 1 || n > 16)
+  {
+    set_error("flag_signal: 1..16 slots");
+    return OIDNB200_ERR_INVALID;
+  }
+  FlagTargets t;
+  t.n = n;
+  for (int i = 0; i < 16; ++i) t.slot[i] = i < n ? static_cast<unsigned int*>(slots[i]) : nullptr;
+  flag_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(t, value);
+  return check_launch("flag_signal");
+}
+
+int oidnb200_flag_wait_launch(const void* flags, int n, unsigned int value, double timeout_s, oidnb200_stream stream)
+{
+  if (!flags || n < 1 || n > 32)
+  {
+    set_error("flag_wait: 1..32 slots");
+    return OIDNB200_ERR_INVALID;
+  }
+  const unsigned long long ns = (unsigned long long)((timeout_s > 0 ? timeout_s : 10.0) * 1e9);
+  flag_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned int*>(flags), n, value, ns);
+  return check_launch("flag_wait");
 }
 
 int oidnb200_pool_launch(const void* src, int H, int W, int C, void* dst, oidnb200_stream stream)

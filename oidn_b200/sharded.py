@@ -139,8 +139,13 @@ class ShardedFilter:
   upload_tiles()); each rank uploads only the source rectangles of its own tiles."""
 
   def __init__(self, dist, torch, device, W, H, tza, hdr=True, quality=api.QUALITY_HIGH, clean_aux=False,
-               aux=True, frame=None, stage=True, source="rank0", own_groups=True):
-    assert source in ("rank0", "distributed")
+               aux=True, frame=None, stage=True, source="rank0", own_groups=True, exchange="peer"):
+    assert source in ("rank0", "distributed") and exchange in ("peer", "nccl")
+    # exchange (distributed frames): "peer" = no collective on the data path -- bin rectangles go to every rank's bin
+    # array by copy-engine peer writes, frame steps are joined with peer flags (oidnb200_flag_signal / _wait: one tiny
+    # block that runs next to a persistent conv CTA); "nccl" = all-reduce of the bin array + 4-byte all-reduce join
+    # (round 1; a collective's kernel holds SMs while it waits for the slowest rank).
+    self.exchange = exchange if source == "distributed" else "nccl"
     self.dist, self.torch, self.dev = dist, torch, device
     self._check_stream()
     self.rank, self.world = dist.get_rank(), dist.get_world_size()
@@ -196,13 +201,27 @@ class ShardedFilter:
     if hdr and source == "rank0" and self.rank == 0:
       self.ae_scratch = torch.zeros(L.oidnb200_autoexposure_scratch_bytes(H, W), dtype=torch.uint8, device="cuda")
       self.ae_img = capi.Image(self.bufs["color"].data, capi.FORMAT_FLOAT3, W, H, 12, 12 * W)
+    nbh, nbw = bin_grid(H, W)
+    self.nbins, self.nbw = nbh * nbw, nbw
     if hdr and source == "distributed":
-      nbh, nbw = bin_grid(H, W)
-      self.nbins = nbh * nbw
       self.bins_local = torch.zeros(self.nbins, dtype=torch.float32, device="cuda")   # zeros outside the own bins
       self.bins_all = torch.zeros(self.nbins, dtype=torch.float32, device="cuda")
       self.bin_rects = [bins_of_tile(t, H, W) for t in self.tiles]
       self.ae_img = capi.Image(self.local["color"].data, capi.FORMAT_FLOAT3, W, H, 12, 12 * W)
+    if self.exchange == "peer":
+      # one exchange buffer per rank, mapped by every rank (CUDA IPC): [bin array][bins-ready flags][frame-done flags]
+      self.off_a = (self.nbins * 4 + 255) // 256 * 256
+      self.off_d = self.off_a + 256
+      xsize = self.off_d + 256
+      self.xb = device.new_buffer(xsize)
+      self.xb.write(np.zeros(xsize, np.uint8))
+      handles = [None] * self.world
+      dist.all_gather_object(handles, self.xb.ipc_handle())
+      self.xpeer = [self.xb if r == self.rank else device.import_buffer(handles[r], xsize) for r in range(self.world)]
+      self.slots_a = (C.c_void_p * self.world)(*[b.data + self.off_a + 4 * self.rank for b in self.xpeer])
+      self.slots_d = (C.c_void_p * self.world)(*[b.data + self.off_d + 4 * self.rank for b in self.xpeer])
+      self.seq = 0
+      dist.barrier()
     if source == "distributed" and frame is not None:
       self.upload_tiles({n: frame[n].ctypes.data for n in self.inputs})
       self.dev.sync()
@@ -259,6 +278,31 @@ class ShardedFilter:
     torch, dist, L = self.torch, self.dist, capi.lib()
     self._check_stream()
     st = torch.cuda.current_stream().cuda_stream
+    if self.source == "distributed" and self.exchange == "peer":
+      def ck(rc):
+        if rc != 0:
+          raise RuntimeError(L.oidnb200_last_error().decode())
+      self.seq += 1
+      if self.hdr:
+        own = self.xb.data
+        for (bh0, bh1, bw0, bw1) in self.bin_rects:
+          ck(L.oidnb200_autoexposure_bins_launch(C.byref(self.ae_img), bh0, bh1, bw0, bw1, own, st))
+        pitch = self.nbw * 4
+        for r, peer in enumerate(self.xpeer):      # the bin rectangles of the own tiles -> every peer's bin array (copy engines)
+          if r == self.rank:
+            continue
+          for (bh0, bh1, bw0, bw1) in self.bin_rects:
+            off = bh0 * pitch + bw0 * 4
+            self.dev.copy_rect_async(peer.data + off, pitch, own + off, pitch, (bw1 - bw0) * 4, bh1 - bh0)
+        ck(L.oidnb200_flag_signal_launch(self.slots_a, self.world, self.seq, st))
+        ck(L.oidnb200_flag_wait_launch(own + self.off_a, self.world, self.seq, 10.0, st))   # every rank's bins are here
+        ck(L.oidnb200_autoexposure_reduce_launch(own, self.nbins, self.scale.data_ptr(), st))
+      self.filter.execute_async()
+      if assemble and self.rank != 0:
+        self._copy_rects(("output",), False)    # NVLink DMA: local interior rectangles -> rank 0's output
+      ck(L.oidnb200_flag_signal_launch(self.slots_d, self.world, self.seq, st))
+      ck(L.oidnb200_flag_wait_launch(self.xb.data + self.off_d, self.world, self.seq, 10.0, st))   # join: the frame is complete everywhere
+      return
     if self.source == "distributed":
       if self.hdr:
         for (bh0, bh1, bw0, bw1) in self.bin_rects:
@@ -294,10 +338,16 @@ class ShardedFilter:
     for b in own:
       b.release()
     self.dist.barrier()
+    if self.exchange == "peer":
+      for r, b in enumerate(self.xpeer):
+        if r != self.rank:
+          b.release()
     if self.rank != 0:
       for b in self.bufs.values():
         b.release()
     self.dist.barrier()
+    if self.exchange == "peer":
+      self.xb.release()
     if self.rank == 0:
       for b in self.bufs.values():
         b.release()
@@ -410,7 +460,7 @@ def bench_main(args, rank, world, local_rank):
   # Two frames in flight (a renderer double-buffers its frame): two device/stream/filter sets, frames
   # alternate between them, so the exchange and the copies of frame f+1 overlap the convolutions of
   # frame f. Collectives are issued in frame order by every rank.
-  def make_sets(source, weights_blob=None, clean_aux=False, policy=None):
+  def make_sets(source, weights_blob=None, clean_aux=False, policy=None, exchange="peer"):
     sets = []
     for _ in range(2):
       stream = torch.cuda.Stream()
@@ -419,7 +469,7 @@ def bench_main(args, rank, world, local_rank):
         if policy is not None:
           dev.set("tilePolicy", policy)
         sf = ShardedFilter(dist, torch, dev, W, H, weights_blob or tza, hdr=True, source=source, clean_aux=clean_aux,
-                           frame=frame if (source == "distributed" or rank == 0) else None)
+                           exchange=exchange, frame=frame if (source == "distributed" or rank == 0) else None)
       sets.append((stream, dev, sf))
     return sets
 
@@ -493,6 +543,15 @@ def bench_main(args, rank, world, local_rank):
                 "value": round(W * H / ms_alt / 1e3, 1), "unit": "Mpix/s"}
     release_sets(alt)
 
+  # round 1's exchange (NCCL all-reduce of the bin array + 4-byte all-reduce join), next to the headline
+  nccl_alt = None
+  if not args.no_rank0:
+    alt = make_sets("distributed", exchange="nccl")
+    ms_alt, _, _ = timed(alt, run_frame)
+    nccl_alt = {"ms_per_step": round(ms_alt, 4), "value": round(W * H / ms_alt / 1e3, 1), "unit": "Mpix/s",
+                "how": "same tiles; bins by NCCL all-reduce, frame join by a 4-byte all-reduce"}
+    release_sets(alt)
+
   sets = make_sets("distributed")
   info = sets[0][2].filter.info()
   ntiles = info["tileCountH"] * info["tileCountW"]
@@ -524,7 +583,7 @@ def bench_main(args, rank, world, local_rank):
            "host_frame": "one frame in POSIX shared memory, page-locked by every rank" if host.shared
                          else "private pinned copy of the frame per rank (/dev/shm too small)",
            "how": "every rank: 2D copies of its tiles' source rectangles (with overlap) from the pinned host frame, sharded "
-                  "execute (autoexposure bins all-reduce), 2D copies of its output rectangles into the host output frame; "
+                  "execute (autoexposure bins by peer writes), 2D copies of its output rectangles into the host output frame; "
                   "all ranks' bytes summed; two frame sets alternating; wall clock, max over ranks"}
   nbins = sets[0][2].nbins
   release_sets(sets)
@@ -594,10 +653,13 @@ def bench_main(args, rank, world, local_rank):
       # all ranks: per tile the filter's ops + one autoexposure-bins launch, per rank one reduce
       # all ranks, per tile: autoexposure bins + input process + the conv launches (a fused pair is one; the output
       # process runs in the last pair's epilogue); per rank one fold of the bin array
-      "gpu_launches": K * (ntiles * (2 + conv_launches // max(ntiles // world, 1)) + world), "clocks": clocks,
-      "exchange": "every rank holds its tiles' inputs (tile + overlap); autoexposure: per-tile bin kernels + NCCL all-reduce of the "
-                  "bin array (%d B) + fixed-order fold on every rank; output rectangles assembled in rank 0's buffer by copy-engine "
-                  "peer writes over NVLink (CUDA IPC); 4-byte all-reduce joins the frame; two frames in flight" % (4 * nbins),
+      # and four flag launches (bins ready: signal + wait, frame done: signal + wait)
+      "gpu_launches": K * (ntiles * (2 + conv_launches // max(ntiles // world, 1)) + 5 * world), "clocks": clocks,
+      "exchange": "every rank holds its tiles' inputs (tile + overlap); autoexposure: per-tile bin kernels, the tiles' bin rectangles "
+                  "go to every rank's bin array (%d B) by copy-engine peer writes, fixed-order fold on every rank; output rectangles "
+                  "assembled in rank 0's buffer by copy-engine peer writes over NVLink (CUDA IPC); frame steps joined with peer flags "
+                  "(one 32-thread block, no collective on the data path); two frames in flight" % (4 * nbins),
+      "exchange_nccl": nccl_alt,
     }
     print(json.dumps(line))
   host.release()

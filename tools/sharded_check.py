@@ -39,24 +39,28 @@ with torch.cuda.stream(stream):
     else:
       sf0.release()
   # distributed frame: every rank holds only its own tiles' source rectangles (the rest of its local
-  # images is garbage), autoexposure by bin all-reduce, output assembled on rank 0 over NVLink
-  sfd = sharded.ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, source="distributed")
+  # images is garbage), autoexposure from every rank's bins, output assembled on rank 0 over NVLink
+  # -- by peer writes of the bin rectangles + peer flags (default) and by NCCL all-reduce; both must give the same bits
   garbage = np.full((H, W, 3), 1e30, np.float32)
-  for n in sfd.inputs:
-    sfd.local[n].write(garbage)
-  sfd.upload_tiles({n: full[n].ctypes.data for n in sfd.inputs})
-  for _ in range(2):
-    sfd.execute_async()
-  torch.cuda.synchronize(); dist.barrier()
-  if rank == 0:
-    o = np.zeros((H, W, 3), np.float32); sfd.bufs["output"].read(o); outs.append(o)
-  scale_d = float(sfd.scale.cpu()[0])
-  sfd.release()
+  scale_d = []
+  for exchange in ("nccl", "peer"):
+    sfd = sharded.ShardedFilter(dist, torch, dev, W, H, tza, hdr=True, source="distributed", exchange=exchange)
+    for n in sfd.inputs:
+      sfd.local[n].write(garbage)
+    sfd.upload_tiles({n: full[n].ctypes.data for n in sfd.inputs})
+    for _ in range(5):
+      sfd.execute_async()
+    torch.cuda.synchronize(); dist.barrier()
+    if rank == 0:
+      o = np.zeros((H, W, 3), np.float32); sfd.bufs["output"].read(o); outs.append(o)
+    scale_d.append(float(sfd.scale.cpu()[0]))
+    sfd.release()
   info = sf.filter.info()
   if rank == 0:
     got = outs[1]
-    same_d = np.array_equal(outs[2].view(np.uint32), outs[1].view(np.uint32))
-    print("distributed frame == frame on rank 0: %s (autoexposure scale %.9g vs %.9g)" % (same_d, scale_d, float(sf.scale.cpu()[0])))
+    same_d = all(np.array_equal(o.view(np.uint32), outs[1].view(np.uint32)) for o in outs[2:])
+    print("distributed frame (nccl, peer exchange) == frame on rank 0: %s (autoexposure scale %.9g, %.9g vs %.9g)"
+          % (same_d, scale_d[0], scale_d[1], float(sf.scale.cpu()[0])))
     ok = np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
     print("staged == direct P2P: %s" % ok)
     ok = ok and same_d
