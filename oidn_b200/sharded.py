@@ -212,7 +212,7 @@ class ShardedFilter:
       # one exchange buffer per rank, mapped by every rank (CUDA IPC): [bin array][bins-ready flags][frame-done flags]
       self.off_a = (self.nbins * 4 + 255) // 256 * 256
       self.off_d = self.off_a + 256
-      xsize = self.off_d + 256
+      xsize = max(self.off_d + 256, 2 << 20)   # an allocation of its own (small cudaMalloc blocks share a 2 MiB page)
       self.xb = device.new_buffer(xsize)
       self.xb.write(np.zeros(xsize, np.uint8))
       handles = [None] * self.world
