@@ -131,6 +131,14 @@ class SharedHostFrame:
     self.images = {}
 
 
+def bin_rect_copies(bin_rects, nbw):
+  """The 2D copies (byte offset, pitch, width in bytes, rows) that carry a rank's bin rectangles from its own bin
+  array (fp32, nbw per row) to the same place in a peer's."""
+  pitch = nbw * 4
+  return [(bh0 * pitch + bw0 * 4, pitch, (bw1 - bw0) * 4, bh1 - bh0) for (bh0, bh1, bw0, bw1) in bin_rects
+          if bh1 > bh0 and bw1 > bw0]
+
+
 class ShardedFilter:
   """RT filter over one frame, executed by all ranks of the process group (see the module docstring).
 
@@ -221,6 +229,7 @@ class ShardedFilter:
       self.slots_a = (C.c_void_p * self.world)(*[b.data + self.off_a + 4 * self.rank for b in self.xpeer])
       self.slots_d = (C.c_void_p * self.world)(*[b.data + self.off_d + 4 * self.rank for b in self.xpeer])
       self.seq = 0
+      self.bin_copies = bin_rect_copies(self.bin_rects, self.nbw) if hdr else []
       dist.barrier()
     if source == "distributed" and frame is not None:
       self.upload_tiles({n: frame[n].ctypes.data for n in self.inputs})
@@ -287,13 +296,11 @@ class ShardedFilter:
         own = self.xb.data
         for (bh0, bh1, bw0, bw1) in self.bin_rects:
           ck(L.oidnb200_autoexposure_bins_launch(C.byref(self.ae_img), bh0, bh1, bw0, bw1, own, st))
-        pitch = self.nbw * 4
         for r, peer in enumerate(self.xpeer):      # the bin rectangles of the own tiles -> every peer's bin array (copy engines)
           if r == self.rank:
             continue
-          for (bh0, bh1, bw0, bw1) in self.bin_rects:
-            off = bh0 * pitch + bw0 * 4
-            self.dev.copy_rect_async(peer.data + off, pitch, own + off, pitch, (bw1 - bw0) * 4, bh1 - bh0)
+          for off, pitch, wbytes, rows in self.bin_copies:
+            self.dev.copy_rect_async(peer.data + off, pitch, own + off, pitch, wbytes, rows)
         ck(L.oidnb200_flag_signal_launch(self.slots_a, self.world, self.seq, st))
         ck(L.oidnb200_flag_wait_launch(own + self.off_a, self.world, self.seq, 10.0, st))   # every rank's bins are here
         ck(L.oidnb200_autoexposure_reduce_launch(own, self.nbins, self.scale.data_ptr(), st))

@@ -84,6 +84,19 @@ def _worker(rank, world, port, q):
       for bi in range(0, nbh, step[0]):
         for bj in range(0, nbw, step[1]):
           assert allb[bi, bj].item() == bin_value(frame, bi, bj), (bi, bj)
+      # the same exchange without a collective (the default): each rank's bin rectangles are copied as 2D byte
+      # rectangles into every peer's array (sharded.bin_rect_copies gives the copies execute_async issues)
+      rects = [sharded.bins_of_tile(t, H, W) for t in mine]
+      copies = [None] * world
+      dist.all_gather_object(copies, (sharded.bin_rect_copies(rects, nbw), mine_bins.tobytes()))
+      peer_view = bytearray(mine_bins.tobytes())
+      for r, (cps, raw) in enumerate(copies):
+        if r == rank:
+          continue
+        for off, pitch, wbytes, rows in cps:
+          for y in range(rows):
+            peer_view[off + y * pitch: off + y * pitch + wbytes] = raw[off + y * pitch: off + y * pitch + wbytes]
+      assert np.array_equal(np.frombuffer(bytes(peer_view), np.float32).reshape(nbh, nbw), allb.numpy())
   # handle exchange: rank 0's 64-byte handles reach every rank unchanged
   handles = {"color": bytes(range(64)), "output": bytes(range(64, 128))} if rank == 0 else None
   got = sharded.broadcast_object(dist, handles, 0)
