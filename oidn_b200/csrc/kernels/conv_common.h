@@ -167,6 +167,8 @@ struct PairKernelParams
   unsigned long long* stamps;       // as ConvKernelParams::stamps
   unsigned long long* trace;        // [22 warps][16 tags] wait-cycle counters (OIDN_B200_TRACE builds), else null
   FusedOutput fo;                   // fo.enabled: B's epilogue writes the output image instead of the tensor
+  int tapB;                         // tap-packed B (3 output channels, fused output): wmapB = [kh][kw * 3 + c][CA], one unshifted
+                                    // view per K step instead of three; the epilogue adds the horizontal taps across lanes
 };
 
 } // namespace oidnb200

@@ -64,8 +64,9 @@ struct PairSmem
   static constexpr uint32_t tmem_ptr  = w_full + 8;
   static constexpr uint32_t bias_a    = 3072;                                   // 64 floats
   static constexpr uint32_t bias_b    = 3072 + 256;                             // 64 floats
+  static constexpr uint32_t xch       = 3072 + 512;                             // tap-packed B: [stream][row parity][warp][8] floats
 };
-static_assert(PairSmem::tmem_ptr + 4 <= PairSmem::bias_a && PairSmem::bias_b + 256 <= kSmemHeader, "barrier block overflows");
+static_assert(PairSmem::tmem_ptr + 4 <= PairSmem::bias_a && PairSmem::xch + 2 * 2 * 4 * 8 * 4 <= kSmemHeader, "barrier block overflows");
 
 struct PItem { int x0, y0, y1; };
 
@@ -83,17 +84,18 @@ __device__ __forceinline__ PItem pair_item(const PairKernelParams& p, int item)
 // One conv's constants for the MMA issuer (descriptor arithmetic in 16-byte units, as conv_tc.cu)
 struct Side
 {
-  uint32_t Cout, R, tbase, max_run, idesc1, hi, nk, row16, b_lo, bblk16, full_bar, empty_bar;
+  uint32_t Cout, R, tbase, max_run, idesc1, hi, nk, row16, b_lo, bblk16, full_bar, empty_bar, ntaps;
 };
 
 template <int NK, bool TWO>
 __device__ __forceinline__ void issue_taps(uint32_t hi, uint32_t a_lo, uint32_t b_lo, uint32_t bblk16, uint32_t d0, uint32_t idesc0,
-                                           uint32_t rb0, uint32_t d1, uint32_t idesc1, uint32_t rb1, bool skip_first)
+                                           uint32_t rb0, uint32_t d1, uint32_t idesc1, uint32_t rb1, bool skip_first, uint32_t ntaps)
 {
   constexpr uint32_t row16 = NK * 2;
 #pragma unroll
   for (int kw = 0; kw < 3; ++kw)
   {
+    if (kw >= (int)ntaps) break;   // tap-packed B: the horizontal taps are columns of the one unshifted view
 #pragma unroll
     for (int j = 0; j < NK; ++j)
     {
@@ -150,15 +152,15 @@ __device__ __forceinline__ void issue_row(const Side& c, bool leader, uint32_t a
     }
     if (n1)
     {
-      if (c.nk == 4)      issue_taps<4, true>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh);
-      else if (c.nk == 2) issue_taps<2, true>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh);
-      else                issue_taps<1, true>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh);
+      if (c.nk == 4)      issue_taps<4, true>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh, c.ntaps);
+      else if (c.nk == 2) issue_taps<2, true>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh, c.ntaps);
+      else                issue_taps<1, true>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh, c.ntaps);
     }
     else
     {
-      if (c.nk == 4)      issue_taps<4, false>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh);
-      else if (c.nk == 2) issue_taps<2, false>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh);
-      else                issue_taps<1, false>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh);
+      if (c.nk == 4)      issue_taps<4, false>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh, c.ntaps);
+      else if (c.nk == 2) issue_taps<2, false>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh, c.ntaps);
+      else                issue_taps<1, false>(c.hi, a_lo, c.b_lo, c.bblk16, d0, idesc_r0, rb0, d1, idesc_r1, rb1, fresh, c.ntaps);
     }
     umma_commit(release_bar);
   }
@@ -282,7 +284,8 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
           for (int kw = 0; kw < 3; ++kw)
           {
             tma_load_4d(w_region + kw * p.wA_blk, &p.wmapA, sbase + PairSmem::w_full, 0, 0, 0, kw);
-            tma_load_4d(w_region + p.wB_off + kw * p.wB_blk, &p.wmapB, sbase + PairSmem::w_full, 0, 0, 0, kw);
+            if (kw == 0 || !p.tapB)
+              tma_load_4d(w_region + p.wB_off + kw * p.wB_blk, &p.wmapB, sbase + PairSmem::w_full, 0, 0, 0, kw);
           }
         }
         pdl_wait();
@@ -313,6 +316,7 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
         A.Cout = (uint32_t)p.CA; A.R = (uint32_t)RA; A.tbase = col0; A.max_run = min(3u, 256u / A.Cout);
         A.idesc1 = umma_idesc_f16(A.Cout); A.hi = p.hiA; A.nk = (uint32_t)p.ccA / 16u; A.row16 = A.nk * 2;
         A.b_lo = sbase16 + (kSmemHeader >> 4); A.bblk16 = p.wA_blk >> 4;
+        A.ntaps = 3;
         A.full_bar = sbase + PairSmem::acca_full + 8 * st * kMaxSlots;
         A.empty_bar = sbase + PairSmem::acca_empty + 8 * st * kMaxSlots;
         const uint32_t a_ring16 = sbase16 + ((kSmemHeader + p.w_bytes_smem + (uint32_t)st * stream_bytes) >> 4);
@@ -359,6 +363,7 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
       B.max_run = min(3u, 256u / B.Cout);
       B.idesc1 = umma_idesc_f16(B.Cout); B.hi = p.hiB; B.nk = (uint32_t)p.CA / 16u; B.row16 = B.nk * 2;
       B.b_lo = sbase16 + ((kSmemHeader + p.wB_off) >> 4); B.bblk16 = p.wB_blk >> 4;
+      B.ntaps = p.tapB ? 1u : 3u;
       B.full_bar = sbase + PairSmem::accb_full + 8 * st * kMaxSlots;
       B.empty_bar = sbase + PairSmem::accb_empty + 8 * st * kMaxSlots;
       const uint32_t m_ring16 = sbase16 + ((kSmemHeader + p.w_bytes_smem + (uint32_t)st * stream_bytes + (uint32_t)NA * p.a_stage_bytes) >> 4);
@@ -487,38 +492,97 @@ conv3x3_pair_kernel(const __grid_constant__ PairKernelParams p)
         const float oscale = output_scale(tf);
         const bool hdr = fo.hdr != 0, snorm = fo.snorm != 0;
         const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2];
-        for (int item = vcta; item < nitems; item += nv)
+        if (p.tapB)
         {
-          const PItem it = pair_item(p, item);
-          const int x = it.x0 + pix;
-          const int xi = x - fo.wSrc;
-          const bool xok = pix < kPairStrip && x < p.W && xi >= 0 && xi < fo.W;
-          ring.begin_item();
-          for (int y = it.y0; y <= it.y1; ++y)
+          // Tap-packed last conv (3 output channels): ONE unshifted view, column kw * 3 + c of a row's accumulator holds
+          // the tap-kw partial sum P[i][kw][c] of the mid pixel i = this TMEM lane. Output pixel i (x = x0 - 1 + i,
+          // i = 1 .. 126) = P[i-1][0] + P[i][1] + P[i+1][2]: neighbours by warp shuffles, across the warps of the
+          // strip through 3 floats of shared memory per side (double-buffered by row, one named barrier per row).
+          float* const xbase = reinterpret_cast<float*>(sgen + PairSmem::xch) + st * 64;
+          uint32_t rowpar = 0;
+          for (int item = vcta; item < nitems; item += nv)
           {
-            uint32_t slot, par;
-            ring.next(slot, par);
-            PWAIT(tfull + 8 * slot, par, 9);
-            tc_fence_after();
-            uint32_t v[4];
-            tmem_ld4(lane_base + slot * (uint32_t)CB, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + 8 * slot);
-            const int yi = y - fo.hSrc;
-            if (xok && yi >= 0 && yi < fo.H)
+            const PItem it = pair_item(p, item);
+            const int x = it.x0 - 1 + pix;
+            const int xi = x - fo.wSrc;
+            const bool xok = pix >= 1 && pix <= kPairStrip && x < p.W && xi >= 0 && xi < fo.W;
+            ring.begin_item();
+            for (int y = it.y0; y <= it.y1; ++y)
             {
-              const float s0 = __uint_as_float(v[0]) + b0, s1 = __uint_as_float(v[1]) + b1, s2 = __uint_as_float(v[2]) + b2;
-              const uint32_t h01 = relu ? pack_half2_relu(s0, s1) : pack_half2(s0, s1);
-              const uint32_t h2x = relu ? pack_half2_relu(s2, 0.f) : pack_half2(s2, 0.f);
-              const __half2 q01 = *reinterpret_cast<const __half2*>(&h01), q2x = *reinterpret_cast<const __half2*>(&h2x);
-              const float3 o = output_pixel(tf, hdr, snorm, false, oscale, __low2float(q01), __high2float(q01), __low2float(q2x));
-              float* d = reinterpret_cast<float*>(fo.ptr + (long long)(yi + fo.hDst) * fo.rs) + (size_t)(xi + fo.wDst) * 3;
-              d[0] = o.x; d[1] = o.y; d[2] = o.z;
+              uint32_t slot, par;
+              ring.next(slot, par);
+              PWAIT(tfull + 8 * slot, par, 9);
+              tc_fence_after();
+              uint32_t v[16];
+              tmem_ld16(lane_base + slot * (uint32_t)CB, v);
+              tmem_ld_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty + 8 * slot);
+              float l0 = __shfl_up_sync(0xffffffffu, __uint_as_float(v[0]), 1);
+              float l1 = __shfl_up_sync(0xffffffffu, __uint_as_float(v[1]), 1);
+              float l2 = __shfl_up_sync(0xffffffffu, __uint_as_float(v[2]), 1);
+              float r0 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[6]), 1);
+              float r1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[7]), 1);
+              float r2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[8]), 1);
+              float* const xb = xbase + rowpar * 32;
+              if (lane == 31) { xb[q * 8 + 0] = __uint_as_float(v[0]); xb[q * 8 + 1] = __uint_as_float(v[1]); xb[q * 8 + 2] = __uint_as_float(v[2]); }
+              if (lane == 0)  { xb[q * 8 + 4] = __uint_as_float(v[6]); xb[q * 8 + 5] = __uint_as_float(v[7]); xb[q * 8 + 6] = __uint_as_float(v[8]); }
+              named_bar_sync(1 + st, 128);
+              if (lane == 0 && q > 0)  { l0 = xb[(q - 1) * 8 + 0]; l1 = xb[(q - 1) * 8 + 1]; l2 = xb[(q - 1) * 8 + 2]; }
+              if (lane == 31 && q < 3) { r0 = xb[(q + 1) * 8 + 4]; r1 = xb[(q + 1) * 8 + 5]; r2 = xb[(q + 1) * 8 + 6]; }
+              rowpar ^= 1;
+              const int yi = y - fo.hSrc;
+              if (xok && yi >= 0 && yi < fo.H)
+              {
+                const float s0 = ((l0 + __uint_as_float(v[3])) + r0) + b0, s1 = ((l1 + __uint_as_float(v[4])) + r1) + b1,
+                            s2 = ((l2 + __uint_as_float(v[5])) + r2) + b2;
+                const uint32_t h01 = relu ? pack_half2_relu(s0, s1) : pack_half2(s0, s1);
+                const uint32_t h2x = relu ? pack_half2_relu(s2, 0.f) : pack_half2(s2, 0.f);
+                const __half2 q01 = *reinterpret_cast<const __half2*>(&h01), q2x = *reinterpret_cast<const __half2*>(&h2x);
+                const float3 o = output_pixel(tf, hdr, snorm, false, oscale, __low2float(q01), __high2float(q01), __low2float(q2x));
+                float* d = reinterpret_cast<float*>(fo.ptr + (long long)(yi + fo.hDst) * fo.rs) + (size_t)(xi + fo.wDst) * 3;
+                d[0] = o.x; d[1] = o.y; d[2] = o.z;
+              }
             }
+            ring.end_item(it.y1 - it.y0 + 1);
           }
-          ring.end_item(it.y1 - it.y0 + 1);
+        }
+        else
+        {
+          for (int item = vcta; item < nitems; item += nv)
+          {
+            const PItem it = pair_item(p, item);
+            const int x = it.x0 + pix;
+            const int xi = x - fo.wSrc;
+            const bool xok = pix < kPairStrip && x < p.W && xi >= 0 && xi < fo.W;
+            ring.begin_item();
+            for (int y = it.y0; y <= it.y1; ++y)
+            {
+              uint32_t slot, par;
+              ring.next(slot, par);
+              PWAIT(tfull + 8 * slot, par, 9);
+              tc_fence_after();
+              uint32_t v[4];
+              tmem_ld4(lane_base + slot * (uint32_t)CB, v);
+              tmem_ld_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty + 8 * slot);
+              const int yi = y - fo.hSrc;
+              if (xok && yi >= 0 && yi < fo.H)
+              {
+                const float s0 = __uint_as_float(v[0]) + b0, s1 = __uint_as_float(v[1]) + b1, s2 = __uint_as_float(v[2]) + b2;
+                const uint32_t h01 = relu ? pack_half2_relu(s0, s1) : pack_half2(s0, s1);
+                const uint32_t h2x = relu ? pack_half2_relu(s2, 0.f) : pack_half2(s2, 0.f);
+                const __half2 q01 = *reinterpret_cast<const __half2*>(&h01), q2x = *reinterpret_cast<const __half2*>(&h2x);
+                const float3 o = output_pixel(tf, hdr, snorm, false, oscale, __low2float(q01), __high2float(q01), __low2float(q2x));
+                float* d = reinterpret_cast<float*>(fo.ptr + (long long)(yi + fo.hDst) * fo.rs) + (size_t)(xi + fo.wDst) * 3;
+                d[0] = o.x; d[1] = o.y; d[2] = o.z;
+              }
+            }
+            ring.end_item(it.y1 - it.y0 + 1);
+          }
         }
       }
       else

@@ -89,7 +89,19 @@ struct ConvPlan
   const void *src1 = nullptr, *src2 = nullptr, *weights = nullptr;
   void* dst = nullptr;
   bool bound = false;
+  CUtensorMap wmap_tap;      // the tap-packed copy of the weights (can_tap_pack), valid once bound
 };
+
+// A 3-channel last conv (dec_conv0 / dec_conv1c) inside a fused pair can take its three horizontal taps as COLUMNS of
+// one MMA instead of three shifted views: per vertical tap a 16-column block holds column kw * 3 + c. A third of the
+// MMAs and of their shared-memory operand reads (the pair kernel's bottleneck); the pair's epilogue adds the three
+// partial sums of neighbouring pixels. The packed weights carry that copy after the regular layout: [kh][16][C1].
+static bool can_tap_pack(const ConvPlan& pl)
+{
+  const oidnb200_conv_desc& d = pl.desc;
+  return d.Cout == 16 && pl.CoutAlloc == 16 && d.C2 == 0 && !d.src1_upsampled && d.post_op == POST_NONE &&
+         pl.kp.nchunks == 1 && pl.kp.ngroups == 1 && (d.C1 == 32 || d.C1 == 64);
+}
 
 static int num_sms()
 {
@@ -434,6 +446,15 @@ static int plan_bind(ConvPlan& pl, const void* src1, const void* src2, const voi
     }
     else
     {
+      if (can_tap_pack(pl))
+      {
+        const uint8_t* wt = static_cast<const uint8_t*>(weights) + (size_t)9 * pl.CoutAlloc * pl.CinTot * 2;
+        const uint64_t td[4] = {(uint64_t)d.C1, 16, 3, 1};
+        const uint64_t ts[3] = {(uint64_t)d.C1 * 2, (uint64_t)16 * d.C1 * 2, (uint64_t)48 * d.C1 * 2};
+        const uint32_t tb[4] = {(uint32_t)cc, 16, 3, 1};
+        rc = encode_tmap(&pl.wmap_tap, wt, 4, td, ts, tb, cc);
+        if (rc) return rc;
+      }
       const uint64_t wd[4] = {(uint64_t)pl.CinTot, (uint64_t)pl.CoutAlloc, 3, 3};
       const uint64_t ws[3] = {(uint64_t)pl.CinTot * 2, (uint64_t)pl.CoutAlloc * pl.CinTot * 2,
                               (uint64_t)3 * pl.CoutAlloc * pl.CinTot * 2};
@@ -547,6 +568,7 @@ struct oidnb200_conv
   std::unique_ptr<ConvPlan> fused_plan;
   // the packed bias as oidnb200_conv_pack_bias produced it (host copy): goes into the kernel parameters at bind
   mutable std::vector<float> host_bias;
+  mutable int tap_O = 0;     // 3 once oidnb200_conv_pack_weights wrote the tap-packed copy (can_tap_pack, 3 output channels)
 };
 
 // Two chained convs as one launch (conv_pair_tc.cu). Refers to the two single-conv ops, which own descriptors,
@@ -559,6 +581,7 @@ struct oidnb200_conv_pair
   int grid = 0;
   size_t smem = 0;
   bool bound = false;
+  bool tap_ok = false;       // conv B has a tap-packed weight copy: used when its output process is fused
 };
 
 static int pair_plan(const oidnb200_conv_desc& da, const ConvPlan& A, const oidnb200_conv_desc& db, const ConvPlan& B,
@@ -674,6 +697,7 @@ int oidnb200_conv_pair_bind(oidnb200_conv_pair* pr)
   kp.out_ptr = B.kp.out_ptr;
   kp.out_W = B.kp.out_W;
   kp.CoutPadB = B.kp.CoutPad;
+  pr->tap_ok = can_tap_pack(B) && pr->b->tap_O == 3 && !kp.poolB && !getenv("OIDN_B200_NO_TAP_PACK");
   pr->bound = true;
   return 0;
 }
@@ -686,6 +710,12 @@ int oidnb200_conv_pair_launch(oidnb200_conv_pair* pr, oidnb200_stream stream)
     return OIDNB200_ERR_INVALID;
   }
   pr->kp.fo = pr->b->plan.kp.fo;            // conv B's fused output process (oidnb200_conv_set_output_process)
+  {
+    PairKernelParams& kp = pr->kp;
+    kp.tapB = (pr->tap_ok && kp.fo.enabled) ? 1 : 0;
+    kp.wmapB = kp.tapB ? pr->b->plan.wmap_tap : pr->b->plan.kp.wmap[0];
+    kp.w_bytes = 3u * kp.wA_blk + (kp.tapB ? 1u : 3u) * kp.wB_blk;
+  }
   pr->kp.stamps = pr->b->plan.kp.stamps;    // in-frame interval of the pair under conv B's entry
   pr->kp.trace = pr->b->plan.kp.trace;
   const cudaError_t e = conv3x3_pair_launch(pr->kp, pr->grid, pr->smem, static_cast<cudaStream_t>(stream));
@@ -738,6 +768,7 @@ size_t oidnb200_conv_weight_bytes(const oidnb200_conv* conv)
   const ConvPlan& pl = conv->plan;
   size_t n = (size_t)9 * pl.CoutAlloc * pl.CinTot;
   if (pl.kp.up_fold) n += (size_t)12 * pl.CoutAlloc * pl.desc.C1;   // [kw][4][CoutAlloc][C1]: vertically pre-summed src1 weights
+  if (can_tap_pack(pl)) n += (size_t)48 * pl.desc.C1;               // [kh][16][C1]: horizontal taps as columns
   return n * sizeof(uint16_t);
 }
 
@@ -767,6 +798,17 @@ int oidnb200_conv_pack_weights(const oidnb200_conv* conv, const uint16_t* w_oihw
           dst[((size_t)(kw * 3 + kh) * pl.CoutAlloc + o) * pl.CinTot + ci] =
             w_oihw[(((size_t)o * I + i) * 3 + kh) * 3 + kw];
     }
+  conv->tap_O = 0;
+  if (can_tap_pack(pl) && O == 3 && I2 == 0)
+  {
+    uint16_t* f = dst + (size_t)9 * pl.CoutAlloc * pl.CinTot;
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I1; ++i)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw)
+            f[((size_t)kh * 16 + (kw * 3 + o)) * pl.desc.C1 + i] = w_oihw[(((size_t)o * I + i) * 3 + kh) * 3 + kw];
+    conv->tap_O = 3;
+  }
   if (pl.kp.up_fold)
   {
     // Row folding of the upsampled src1: upsampled rows 2Y and 2Y+1 are both low-res row Y. At the even virtual row

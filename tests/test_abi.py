@@ -230,3 +230,37 @@ def test_row_folding_plan_and_weights_without_gpu(monkeypatch):
   for j, st in enumerate(stacks):
     np.testing.assert_array_equal(fol[:, j, :O, :I1], st.astype(np.float16).transpose(2, 0, 1))
   assert not fol[:, :, O:].any() and not fol[:, :, :, I1:].any()      # padding stays zero
+
+
+def test_tap_packed_last_conv_weights_without_gpu():
+  """The 3-channel last conv of a fused pair (dec_conv0 / dec_conv1c): oidnb200_conv_pack_weights appends a copy with the
+  horizontal taps as columns, [kh][kw * 3 + c (16 columns)][C1], behind the regular [kw][kh][16][C1] block; other
+  convs do not carry it."""
+  L = capi.lib()
+
+  def make(H, W, C1, C2, Co, post=0):
+    d = capi.ConvDesc(H, W, C1, C2, Co, 1, post, 0, 0)
+    h = C.c_void_p()
+    assert L.oidnb200_conv_create(C.byref(d), C.byref(h)) == 0, L.oidnb200_last_error()
+    return h
+
+  for C1 in (32, 64):
+    last = make(2160, 3840, C1, 0, 16)
+    assert L.oidnb200_conv_weight_bytes(last) == (9 * 16 * C1 + 48 * C1) * 2
+    rng = np.random.default_rng(C1)
+    w = (rng.standard_normal((3, C1, 3, 3)) * 0.1).astype(np.float16)
+    buf = np.full(L.oidnb200_conv_weight_bytes(last) // 2, np.nan, np.float16)
+    assert L.oidnb200_conv_pack_weights(last, w.ctypes.data, 3, C1, 0, buf.ctypes.data) == 0
+    reg = buf[:9 * 16 * C1].reshape(3, 3, 16, C1)                     # [kw][kh][o][ci]
+    tap = buf[9 * 16 * C1:].reshape(3, 16, C1)                        # [kh][kw * 3 + o][ci]
+    np.testing.assert_array_equal(reg[:, :, :3], w.transpose(3, 2, 0, 1))
+    for kh in range(3):
+      for kw in range(3):
+        np.testing.assert_array_equal(tap[kh, kw * 3:kw * 3 + 3], w[:, :, kh, kw])
+    assert not tap[:, 9:].any() and not reg[:, :, 3:].any()
+    # a 4-channel output does not fit 3 taps x C <= 16 columns per row: the copy stays zero and is not used
+    w4 = (rng.standard_normal((4, C1, 3, 3)) * 0.1).astype(np.float16)
+    assert L.oidnb200_conv_pack_weights(last, w4.ctypes.data, 4, C1, 0, buf.ctypes.data) == 0
+    assert not buf[9 * 16 * C1:].any()
+  assert L.oidnb200_conv_weight_bytes(make(2160, 3840, 32, 0, 32)) == 9 * 32 * 32 * 2     # not a 16-column conv
+  assert L.oidnb200_conv_weight_bytes(make(2160, 3840, 48, 0, 16)) == 9 * 16 * 48 * 2     # source width not covered

@@ -386,6 +386,67 @@ def test_conv_pair_bit_identical_to_two_launches(case):
   assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
 
 
+TAP_CASES = [(33, 127, 64, 32), (40, 253, 32, 32), (21, 260, 64, 64), (300, 140, 64, 32), (1, 1, 64, 32), (3, 126, 64, 32),
+             (7, 126 * 3 + 1, 64, 32), (2, 64, 32, 32)]
+
+
+@pytest.mark.parametrize("case", TAP_CASES, ids=["%dx%d_%d_%d" % c for c in TAP_CASES])
+@pytest.mark.parametrize("tf,hdr", [(capi.TF_LINEAR, 0), (capi.TF_PU, 1)])
+def test_conv_pair_tap_packed_last_conv(case, tf, hdr, monkeypatch):
+  """The 3-channel last conv of a pair with the output process fused takes its horizontal taps as accumulator COLUMNS
+  (one MMA view instead of three) and its epilogue adds the three partial sums of neighbouring pixels, across lanes and
+  across the warps of a strip. The fp32 sums associate differently from the single accumulator of the two-launch
+  path, so the fp16-rounded network output may differ by one fp16 step in a few pixels -- nothing more; with
+  OIDN_B200_NO_TAP_PACK the pair is bit-identical to two launches. Nothing outside the tile's rectangle is written."""
+  H, W, IA, CA = case
+  L = capi.lib()
+  rng = np.random.default_rng(hash(case) & 0xFFFF)
+  src = torch.from_numpy(_rand_half(rng, (H, W, IA))).cuda()
+  wa = (rng.standard_normal((CA, IA, 3, 3)) * np.sqrt(2.0 / (9 * IA))).astype(np.float16)
+  ba = (rng.random(CA) * 0.2 - 0.1).astype(np.float16)
+  wb = (rng.standard_normal((3, CA, 3, 3)) * np.sqrt(1.0 / (9 * CA))).astype(np.float16)
+  bb = np.array([0.4, 0.5, 0.05], np.float16)
+  tile = dict(hSrcBegin=0, wSrcBegin=0, hDstBegin=2, wDstBegin=3, H=H, W=W)
+  if H > 20:
+    tile = dict(hSrcBegin=3, wSrcBegin=5, hDstBegin=2, wDstBegin=3, H=H - 7, W=W - 9)
+  gt = capi.Tile(*[tile[n] for n, _ in capi.Tile._fields_])
+  gtf = capi.Transfer(tf, 0.25 if hdr else 1.0, None)
+  IH, IW = H + 4, W + 6
+  st = torch.cuda.current_stream().cuda_stream
+  a = ConvOp(H, W, IA, 0, CA, relu=1)
+  mid = a.run(src, None, wa, ba, IA, 0)
+  img_ref = torch.full((IH, IW, 3), -7.0, dtype=torch.float32, device="cuda")
+  b = ConvOp(H, W, CA, 0, 16, relu=0)
+  b.run(mid, None, wb, bb, CA, 0, fused=(gt, gtf, hdr, 0, image_of(img_ref)))
+  imgs = {}
+  for mode in ("tap", "regular"):
+    if mode == "regular":
+      monkeypatch.setenv("OIDN_B200_NO_TAP_PACK", "1")
+    img = torch.full((IH, IW, 3), -7.0, dtype=torch.float32, device="cuda")
+    check(L.oidnb200_conv_set_output_process(b.h, C.byref(gt), C.byref(gtf), hdr, 0, C.byref(image_of(img))))
+    pair = C.c_void_p()
+    check(L.oidnb200_conv_pair_create(a.h, b.h, C.byref(pair)))
+    check(L.oidnb200_conv_pair_bind(pair))
+    check(L.oidnb200_conv_pair_launch(pair, st))
+    torch.cuda.synchronize()
+    L.oidnb200_conv_pair_destroy(pair)
+    imgs[mode] = img.cpu().numpy()
+  ref = img_ref.cpu().numpy()
+  np.testing.assert_array_equal(imgs["regular"].view(np.uint32), ref.view(np.uint32))
+  inside = np.zeros((IH, IW), bool)
+  inside[tile["hDstBegin"]:tile["hDstBegin"] + tile["H"], tile["wDstBegin"]:tile["wDstBegin"] + tile["W"]] = True
+  got = imgs["tap"]
+  assert np.all(got[~inside] == -7.0) and np.all(got[inside] != -7.0)
+  if tf == capi.TF_LINEAR:
+    # the image is the fp16 network output itself (clamped to [0, 1]): at most one fp16 step apart, or, where the taps
+    # cancel to almost nothing, the fp32 rounding of the partial sums (~0.5 each)
+    step = np.maximum(np.abs(ref[inside]), 2.0 ** -14) * 2.0 ** -10
+    assert np.all(np.abs(got[inside] - ref[inside]) <= step * 1.001 + 1e-6)
+  else:
+    np.testing.assert_allclose(got[inside], ref[inside], rtol=2e-2, atol=1e-4)   # PU inverse of a one-step difference
+  assert np.mean(got[inside] != ref[inside]) < 0.05
+
+
 def test_conv_pair_rejects_what_it_does_not_cover():
   L = capi.lib()
   def pair_rc(da, db):
