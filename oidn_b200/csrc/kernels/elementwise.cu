@@ -352,6 +352,7 @@ struct AeBinsParams
   int nbh, nbw;             // bin grid of the whole image
   int bh0, bh1, bw0, bw1;   // rectangle of bins computed by this launch
   float* bins;              // [nbh * nbw]
+  int narrow;               // nbh * H and nbw * W fit 32 bits: the bin bounds take 32-bit divisions
 };
 
 constexpr int kAeThreads = 256;
@@ -367,8 +368,19 @@ __global__ void __launch_bounds__(kAeThreads) autoexposure_bins_kernel(const AeB
   for (int bin = blockIdx.x * nwarps + warp; bin < nbins; bin += gridDim.x * nwarps)
   {
     const int bi = p.bh0 + bin / rw, bj = p.bw0 + bin % rw;
-    const int h0 = (int)((long long)bi * p.src.H / p.nbh), h1 = (int)((long long)(bi + 1) * p.src.H / p.nbh);
-    const int w0 = (int)((long long)bj * p.src.W / p.nbw), w1 = (int)((long long)(bj + 1) * p.src.W / p.nbw);
+    int h0, h1, w0, w1;
+    if (p.narrow)
+    {
+      // (bin index + 1) x image size < 2^32 (every image below 128K pixels a side): 32-bit divisions -- the four
+      // 64-bit ones were a third of this kernel's issue slots
+      h0 = (int)((unsigned)bi * (unsigned)p.src.H / (unsigned)p.nbh); h1 = (int)((unsigned)(bi + 1) * (unsigned)p.src.H / (unsigned)p.nbh);
+      w0 = (int)((unsigned)bj * (unsigned)p.src.W / (unsigned)p.nbw); w1 = (int)((unsigned)(bj + 1) * (unsigned)p.src.W / (unsigned)p.nbw);
+    }
+    else
+    {
+      h0 = (int)((long long)bi * p.src.H / p.nbh); h1 = (int)((long long)(bi + 1) * p.src.H / p.nbh);
+      w0 = (int)((long long)bj * p.src.W / p.nbw); w1 = (int)((long long)(bj + 1) * p.src.W / p.nbw);
+    }
     float L = 0.f;
     const int w = w0 + col;
     // a bin has at most 16 rows = 8 per lane half: all 8 row loads are issued before the first use
@@ -662,6 +674,7 @@ int oidnb200_autoexposure_bins_launch(const oidnb200_image* src, int bin_h0, int
   }
   p.bh0 = bin_h0; p.bh1 = bin_h1; p.bw0 = bin_w0; p.bw1 = bin_w1;
   p.bins = bins;
+  p.narrow = ((unsigned long long)p.nbh * p.src.H < (1ull << 32) && (unsigned long long)p.nbw * p.src.W < (1ull << 32)) ? 1 : 0;
   const int n = (bin_h1 - bin_h0) * (bin_w1 - bin_w0);
   if (n == 0) return 0;
   autoexposure_bins_kernel<<<autoexposure_grid(n), kAeThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
