@@ -413,7 +413,16 @@ def test_staged_half_and_row_strided_host_images():
     wide_c = torch.zeros((H, W, 4), dtype=dtype).pin_memory(); wide_c[:, :, :3] = c
     wide_o = torch.zeros((H, W, 4), dtype=dtype).pin_memory()
     assert run(wide_c[:, :, :3], wide_o[:, :, :3])["staged"] == 0
-    assert torch.equal(wide_o[:, :, :3], ref.cpu()) and not bool(wide_o[:, :, 3].any())
+    assert not bool(wide_o[:, :, 3].any())
+    if dtype == torch.float16:
+      assert torch.equal(wide_o[:, :, :3], ref.cpu())
+    else:
+      # a 16-byte fp32 pixel is not written by the fused output process, so the last conv runs un-packed here and
+      # tap-packed in `ref` (tests/test_ops_gpu.py::test_conv_pair_tap_packed_last_conv): one fp16 step of the network
+      # output in a few pixels, through the sRGB inverse (x = y^2.4)
+      a, b = wide_o[:, :, :3].numpy(), ref.cpu().numpy()
+      assert np.mean(a != b) < 0.05
+      np.testing.assert_allclose(a, b, rtol=5e-3, atol=1e-5)
   # one channel
   c1 = torch.from_numpy(color[:, :, :1].copy())
   ref1 = torch.zeros((H, W, 1), device="cuda")
