@@ -59,7 +59,9 @@ typedef struct oidnb200_conv oidnb200_conv;
 OIDNB200_API int oidnb200_conv_create(const oidnb200_conv_desc* desc, oidnb200_conv** out);
 OIDNB200_API void oidnb200_conv_destroy(oidnb200_conv* conv);
 
-/* Bytes of the packed (device-layout) weight and bias buffers. */
+/* Bytes of the packed (device-layout) weight and bias buffers. The weight buffer holds the regular layout
+ * [kw][kh][Cout][Cin] and, for the convs that use them, derived copies behind it: the vertically pre-summed rows of an
+ * upsampled source (row folding) and the tap-packed copy [kh][kw * 3 + c][Cin] of a 3-channel last conv (fused pairs). */
 OIDNB200_API size_t oidnb200_conv_weight_bytes(const oidnb200_conv* conv);
 OIDNB200_API size_t oidnb200_conv_bias_bytes(const oidnb200_conv* conv);
 

@@ -11,11 +11,16 @@ holding the frame:
     what a multi-GPU renderer produces, and what each rank pulls from host memory over its own PCIe
     link in the end-to-end path. The one global value, the autoexposure scale, is exchanged exactly:
     each rank computes log2(mean luminance) of the <=16x16 bins of its tiles
-    (oidnb200_autoexposure_bins_launch) into a zero-filled bin array, an NCCL all-reduce (sum; x + 0
-    = x, ~0.5 MB at 8K) completes the array on every rank, and every rank folds it in the same fixed
-    order (oidnb200_autoexposure_reduce_launch) -- bit-identical to one GPU. Output rectangles are
-    assembled in rank 0's output buffer with copy-engine peer writes over NVLink (CUDA IPC mapping),
-    or go straight to the host frame in the end-to-end path. A 4-byte all-reduce joins the frame.
+    (oidnb200_autoexposure_bins_launch) into its bin array, copy engines write those bin rectangles
+    into every peer's array (CUDA IPC mapping; ~0.5 MB per array at 8K), and once every rank's
+    rectangles have arrived every rank folds the array in the same fixed order
+    (oidnb200_autoexposure_reduce_launch) -- bit-identical to one GPU. Output rectangles are
+    assembled in rank 0's output buffer with copy-engine peer writes over NVLink, or go straight to
+    the host frame in the end-to-end path. The two ordering points of a frame ("all bins are here",
+    "the frame is complete everywhere") are peer flags: oidnb200_flag_signal_launch stores the
+    frame's sequence number into this rank's slot on every rank, oidnb200_flag_wait_launch polls
+    the local slots -- no collective on the data path (exchange="peer", default). exchange="nccl"
+    does the same with an all-reduce of a zero-filled bin array (x + 0 = x) and a 4-byte all-reduce.
 
   source="rank0": the whole frame (color/albedo/normal/output) lives in rank 0's HBM (the
     single-pointer contract of oidnSetSharedFilterImage); rank 0 exports the four buffers as CUDA IPC
