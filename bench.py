@@ -367,6 +367,7 @@ def main():
       e2e = bench_e2e_staged(api, torch, local_rank, imgs, tza, W, H, K, Wm)
       e2e_alt = bench_e2e(api, torch, local_rank, imgs, tza, W, H, K, Wm)
     dev.release()
+    in_flight = None if args.no_e2e else bench_frames_in_flight(api, torch, local_rank, imgs, tza, W, H, K, Wm)
 
     # ---- the other single-GPU lines of BASELINE.json's metric: the 8K frame (base of the 1->N scaling curve) and
     # config 3's model (large UNet: cleanAux + quality=high) on it ------------------------------------------------
@@ -383,10 +384,57 @@ def main():
     "dtype": "f16", "accumulate": "f32", "data": "synthetic",
     "config": dict(workload_config(args, 1), tiles="%dx%d of %dx%d" % (info["tileCountW"], info["tileCountH"], info["tileW"], info["tileH"])),
     "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "passes": passes,
-    "e2e_caller_double_buffered": e2e_alt, "kernel_to_beat": kernel_to_beat,
+    "e2e_caller_double_buffered": e2e_alt, "kernel_to_beat": kernel_to_beat, "three_frames_in_flight": in_flight,
   }
   line.update(extra)
   print(json.dumps(line))
+
+
+def bench_frames_in_flight(api, torch, gpu, imgs, tza, W, H, K, Wm, nsets=3):
+  """Device-resident throughput with several frames in flight (a renderer that owns several frame buffers): nsets
+  device/stream/filter sets on the one GPU, frames alternate between them, so the autoexposure + input process and
+  the first convs of frame f+1 run under the low-resolution layers of frame f, whose persistent grids leave SMs idle.
+  Reported NEXT to the headline, which stays one frame at a time on one filter."""
+  nb = W * H * 12
+  sets = []
+  for _ in range(nsets):
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+      d = api.Device((gpu,), streams=[s.cuda_stream]).commit()
+      bufs = {k: d.new_buffer(nb) for k in ("color", "albedo", "normal", "output")}
+      for k, v in imgs.items():
+        bufs[k].write(v)
+      f = d.new_filter("RT")
+      for k, b in bufs.items():
+        f.set_image(k, b, api.capi.FORMAT_FLOAT3, W, H)
+      f.set("hdr", True); f.set("quality", api.QUALITY_HIGH); f.set_data("weights", tza); f.commit()
+    sets.append((s, d, bufs, f))
+
+  def frame(i):
+    with torch.cuda.stream(sets[i % nsets][0]):
+      sets[i % nsets][3].execute_async()
+
+  for i in range(max(Wm, nsets) + nsets):
+    frame(i)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(sets[0][0])
+  for s, *_ in sets[1:]:
+    s.wait_event(e0)
+  for i in range(K):
+    frame(i)
+  for s, *_ in sets[1:]:
+    join = torch.cuda.Event(); join.record(s); sets[0][0].wait_event(join)
+  e1.record(sets[0][0])
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / K
+  for s, d, bufs, f in sets:
+    f.release()
+    for b in bufs.values():
+      b.release()
+    d.release()
+  return {"sets": nsets, "ms_per_step": round(ms, 4), "value": round(W * H / ms / 1e3, 1), "unit": "Mpix/s",
+          "how": "%d device/stream/filter sets on one GPU, frames alternate; CUDA events around K frames" % nsets}
 
 
 def bench_e2e_staged(api, torch, gpu, imgs, tza, W, H, K, Wm, gpus=None):
