@@ -11,7 +11,7 @@ holding the frame:
     what a multi-GPU renderer produces, and what each rank pulls from host memory over its own PCIe
     link in the end-to-end path. The one global value, the autoexposure scale, is exchanged exactly:
     each rank computes log2(mean luminance) of the <=16x16 bins of its tiles
-    (oidnb200_autoexposure_bins_launch) into its bin array, copy engines write those bin rectangles
+    (oidnb200_autoexposure_bins_launch) into its bin array, a copy kernel stores those bin rectangles
     into every peer's array (CUDA IPC mapping; ~0.5 MB per array at 8K), and once every rank's
     rectangles have arrived every rank folds the array in the same fixed order
     (oidnb200_autoexposure_reduce_launch) -- bit-identical to one GPU. Output rectangles are
@@ -158,6 +158,7 @@ class ShardedFilter:
     # array by copy-engine peer writes, frame steps are joined with peer flags (oidnb200_flag_signal / _wait: one tiny
     # block that runs next to a persistent conv CTA); "nccl" = all-reduce of the bin array + 4-byte all-reduce join
     # (round 1; a collective's kernel holds SMs while it waits for the slowest rank).
+    exchange = os.environ.get("OIDN_B200_EXCHANGE", exchange)    # A/B on one box
     self.exchange = exchange if source == "distributed" else "nccl"
     self.dist, self.torch, self.dev = dist, torch, device
     self._check_stream()
@@ -235,6 +236,12 @@ class ShardedFilter:
       self.slots_d = (C.c_void_p * self.world)(*[b.data + self.off_d + 4 * self.rank for b in self.xpeer])
       self.seq = 0
       self.bin_copies = bin_rect_copies(self.bin_rects, self.nbw) if hdr else []
+      self.bin_scatter = []     # (source rectangle in the own array, the same rectangle in a peer's) as 1-channel fp32 images
+      for r, peer in enumerate(self.xpeer):
+        if r != self.rank:
+          for off, pitch, wbytes, rows in self.bin_copies:
+            self.bin_scatter.append((capi.Image(self.xb.data + off, capi.FORMAT_FLOAT, wbytes // 4, rows, 4, pitch),
+                                     capi.Image(peer.data + off, capi.FORMAT_FLOAT, wbytes // 4, rows, 4, pitch)))
       dist.barrier()
     if source == "distributed" and frame is not None:
       self.upload_tiles({n: frame[n].ctypes.data for n in self.inputs})
@@ -301,11 +308,11 @@ class ShardedFilter:
         own = self.xb.data
         for (bh0, bh1, bw0, bw1) in self.bin_rects:
           ck(L.oidnb200_autoexposure_bins_launch(C.byref(self.ae_img), bh0, bh1, bw0, bw1, own, st))
-        for r, peer in enumerate(self.xpeer):      # the bin rectangles of the own tiles -> every peer's bin array (copy engines)
-          if r == self.rank:
-            continue
-          for off, pitch, wbytes, rows in self.bin_copies:
-            self.dev.copy_rect_async(peer.data + off, pitch, own + off, pitch, wbytes, rows)
+        # the bin rectangles of the own tiles -> every peer's bin array. By a copy KERNEL (peer stores), not the copy
+        # engines: those are busy with the frame's bulk transfers (output rectangles, and in the end-to-end path the PCIe
+        # uploads of the other frame in flight), and every rank's frame waits for these few kilobytes
+        for src_img, dst_img in self.bin_scatter:
+          ck(L.oidnb200_image_copy_launch(C.byref(src_img), C.byref(dst_img), st))
         ck(L.oidnb200_flag_signal_launch(self.slots_a, self.world, self.seq, st))
         ck(L.oidnb200_flag_wait_launch(own + self.off_a, self.world, self.seq, 10.0, st))   # every rank's bins are here
         ck(L.oidnb200_autoexposure_reduce_launch(own, self.nbins, self.scale.data_ptr(), st))
@@ -668,7 +675,7 @@ def bench_main(args, rank, world, local_rank):
       # and four flag launches (bins ready: signal + wait, frame done: signal + wait)
       "gpu_launches": K * (ntiles * (2 + conv_launches // max(ntiles // world, 1)) + 5 * world), "clocks": clocks,
       "exchange": "every rank holds its tiles' inputs (tile + overlap); autoexposure: per-tile bin kernels, the tiles' bin rectangles "
-                  "go to every rank's bin array (%d B) by copy-engine peer writes, fixed-order fold on every rank; output rectangles "
+                  "go to every rank's bin array (%d B) by peer stores of a copy kernel, fixed-order fold on every rank; output rectangles "
                   "assembled in rank 0's buffer by copy-engine peer writes over NVLink (CUDA IPC); frame steps joined with peer flags "
                   "(one 32-thread block, no collective on the data path); two frames in flight" % (4 * nbins),
       "exchange_nccl": nccl_alt,
