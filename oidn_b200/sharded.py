@@ -672,8 +672,9 @@ def bench_main(args, rank, world, local_rank):
       # all ranks: per tile the filter's ops + one autoexposure-bins launch, per rank one reduce
       # all ranks, per tile: autoexposure bins + input process + the conv launches (a fused pair is one; the output
       # process runs in the last pair's epilogue); per rank one fold of the bin array
-      # and four flag launches (bins ready: signal + wait, frame done: signal + wait)
-      "gpu_launches": K * (ntiles * (2 + conv_launches // max(ntiles // world, 1)) + 5 * world), "clocks": clocks,
+      # and four flag launches (bins ready: signal + wait, frame done: signal + wait); per rank and peer one bin-scatter
+      # copy kernel per tile
+      "gpu_launches": K * (ntiles * (2 + conv_launches // max(ntiles // world, 1)) + 5 * world + (world - 1) * ntiles), "clocks": clocks,
       "exchange": "every rank holds its tiles' inputs (tile + overlap); autoexposure: per-tile bin kernels, the tiles' bin rectangles "
                   "go to every rank's bin array (%d B) by peer stores of a copy kernel, fixed-order fold on every rank; output rectangles "
                   "assembled in rank 0's buffer by copy-engine peer writes over NVLink (CUDA IPC); frame steps joined with peer flags "
