@@ -205,3 +205,24 @@ def test_unet_arena_is_close_to_the_live_peak():
   total, _ = plan_arena([x[0] for x in t], [x[1] for x in t], [x[2] for x in t])
   peak = max(sum(s for s, f, l in t if f <= op <= l) for op in range(18))
   assert peak <= total <= 1.15 * peak, (total, peak)
+
+
+def test_bench_reference_arm_contract():
+  """`bench.py --impl reference` (the driver's reference arm): the oracle port on host cores, one JSON line with the
+  contract's keys -- `impl`, the metric / unit of the product arm, a `cpu_baseline` describing the run and an `e2e`
+  that repeats the value with zero transfer bytes. A tiny frame keeps it to a second; no GPU involved."""
+  import json
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--width", "96", "--height", "64",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+  assert out.returncode == 0, out.stderr[-500:]
+  line = json.loads(out.stdout.strip().splitlines()[-1])
+  assert line["impl"] == "reference" and line["unit"] == "Mpix/s" and line["higher_is_better"] is True
+  assert line["n_gpus"] == 1 and line["steps"] == 1 and line["vs_baseline"] is None and line["value"] > 0
+  assert line["config"]["width"] == 96 and line["config"]["height"] == 64 and "workload" in line["config"]
+  cb = line["cpu_baseline"]
+  assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+  assert line["e2e"] == {"value": line["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
