@@ -226,3 +226,25 @@ def test_bench_reference_arm_contract():
   cb = line["cpu_baseline"]
   assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
   assert line["e2e"] == {"value": line["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_under_torchrun_prints_once():
+  """N > 1: the driver launches the reference arm like the product arm (torchrun, one rank per GPU); rank 0 alone runs
+  and prints the line, the other ranks exit 0 without work."""
+  import json
+  import os
+  import socket
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+  out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--width", "96", "--height", "64", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+  assert out.returncode == 0, out.stderr[-500:]
+  lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+  assert len(lines) == 1
+  line = json.loads(lines[0])
+  assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
